@@ -1,0 +1,209 @@
+// PWC-Net 9x9 cost volume (81 displacements, zero padding 4, mean over channels), forward + backward, sm_100a.
+//
+// Replaces OpticalFlow/correlation.py:17-242 (rearrange x2 + updateOutput; updateGradFirst / updateGradSecond
+// launched once per sample).  No NHWC scratch copies: tiles of the NCHW inputs are staged in shared memory
+// with their 4-pixel halo and zero fill, and every thread register-blocks 4 pixels x 3 dy x 9 dx.
+#include "common.cuh"
+
+namespace fldr {
+
+constexpr int kPad = 4;
+constexpr int kD = 9;
+
+// ------------------------------------------------------------------------------------------------
+// Forward.  CTA = 32 x 8 output pixels, 192 threads: thread = (4-pixel group, row, dy-group of 3).
+// Per channel and thread: 1 LDS.128 (first) + 9 LDS.128 (second, 3 rows x 12 floats) feed 108 FFMA.
+// ------------------------------------------------------------------------------------------------
+namespace fwd {
+constexpr int TW = 32, TH = 8, CK = 8, NT = 192;
+constexpr int F2W = TW + 2 * kPad, F2H = TH + 2 * kPad;
+}  // namespace fwd
+
+__global__ void __launch_bounds__(fwd::NT) corr81_fwd_kernel(View4 f1, View4 f2, float* __restrict__ out, int C, int H,
+                                                             int W) {
+    using namespace fwd;
+    __shared__ __align__(16) float s1[CK][TH][TW];
+    __shared__ __align__(16) float s2[CK][F2H][F2W];
+    const int tid = threadIdx.x;
+    const int pg = tid & 7, row = (tid >> 3) & 7, dyg = tid >> 6;
+    const int x0t = blockIdx.x * TW, y0t = blockIdx.y * TH, b = blockIdx.z;
+    const float* p1 = f1.p + b * f1.sn;
+    const float* p2 = f2.p + b * f2.sn;
+
+    float acc[3][kD][4];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int o = 0; o < kD; ++o)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[d][o][j] = 0.f;
+
+    for (int c0 = 0; c0 < C; c0 += CK) {
+        __syncthreads();
+        for (int e = tid; e < CK * TH * TW; e += NT) {
+            const int c = e / (TH * TW), r = (e / TW) % TH, xx = e % TW;
+            const int gy = y0t + r, gx = x0t + xx;
+            float v = 0.f;
+            if (c0 + c < C && gy < H && gx < W) v = __ldg(p1 + (c0 + c) * f1.sc + gy * f1.sh + gx * f1.sw);
+            s1[c][r][xx] = v;
+        }
+        for (int e = tid; e < CK * F2H * F2W; e += NT) {
+            const int c = e / (F2H * F2W), r = (e / F2W) % F2H, xx = e % F2W;
+            const int gy = y0t + r - kPad, gx = x0t + xx - kPad;
+            float v = 0.f;
+            if (c0 + c < C && gy >= 0 && gy < H && gx >= 0 && gx < W)
+                v = __ldg(p2 + (c0 + c) * f2.sc + gy * f2.sh + gx * f2.sw);
+            s2[c][r][xx] = v;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int c = 0; c < CK; ++c) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&s1[c][row][pg * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const float4* rp = reinterpret_cast<const float4*>(&s2[c][row + dyg * 3 + d][pg * 4]);
+                const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
+                const float f[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+                for (int o = 0; o < kD; ++o)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[d][o][j] = fmaf(a[j], f[j + o], acc[d][o][j]);
+            }
+        }
+    }
+
+    const int y = y0t + row, x = x0t + pg * 4;
+    if (y >= H || x >= W) return;
+    const float fc = (float)C;
+    const long long HW = (long long)H * W;
+    float* ob = out + (long long)b * 81 * HW + (long long)y * W + x;
+    const bool vec = ((W & 3) == 0) && (x + 3 < W);
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int o = 0; o < kD; ++o) {
+            float* op = ob + (long long)((dyg * 3 + d) * kD + o) * HW;
+            if (vec) {
+                *reinterpret_cast<float4*>(op) =
+                    make_float4(acc[d][o][0] / fc, acc[d][o][1] / fc, acc[d][o][2] / fc, acc[d][o][3] / fc);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (x + j < W) op[j] = acc[d][o][j] / fc;
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward (first version: one batched launch per gradient instead of the reference's launch per sample,
+// NCHW-coalesced stores, grad_out kept in registers across a chunk of channels).
+//   gF1[b,c,y,x] = (1/C) sum_{p,o} gOut[b,op,y,x]     * f2z[b,c,y+p,x+o]               (correlation.py:151-169)
+//   gF2[b,c,y,x] = (1/C) sum_{p,o} gOut[b,op,y-p,x-o] * f1 [b,c,y-p,x-o]  (in frame)   (correlation.py:200-236)
+// ------------------------------------------------------------------------------------------------
+constexpr int kBwdChunk = 16;
+
+template <bool kSecond>
+__global__ void __launch_bounds__(128) corr81_bwd_kernel(View4 feat, View4 gout, float* __restrict__ grad, int C, int H,
+                                                         int W, int nchunks) {
+    const long long HW = (long long)H * W;
+    const long long per_b = HW * nchunks;
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (idx >= per_b) return;
+    const int x = (int)(idx % W);
+    const int y = (int)((idx / W) % H);
+    const int chunk = (int)(idx / HW);
+    const float* gp = gout.p + b * gout.sn;
+    const float* fp = feat.p + b * feat.sn;
+
+    float g[81];
+#pragma unroll
+    for (int p = 0; p < kD; ++p)
+#pragma unroll
+        for (int o = 0; o < kD; ++o) {
+            // first: grad_out at (y, x); second: grad_out at the source pixel (y-p', x-o')
+            const int yy = kSecond ? y - (p - kPad) : y;
+            const int xx = kSecond ? x - (o - kPad) : x;
+            float v = 0.f;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(gp + (p * kD + o) * gout.sc + yy * gout.sh + xx * gout.sw);
+            g[p * kD + o] = v;
+        }
+    const float fc = (float)C;
+    const int c_end = min(C, (chunk + 1) * kBwdChunk);
+    for (int c = chunk * kBwdChunk; c < c_end; ++c) {
+        const float* fpc = fp + c * feat.sc;
+        float sum = 0.f;
+#pragma unroll
+        for (int p = 0; p < kD; ++p) {
+            const int yy = kSecond ? y - (p - kPad) : y + (p - kPad);
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int o = 0; o < kD; ++o) {
+                const int xx = kSecond ? x - (o - kPad) : x + (o - kPad);
+                if (xx >= 0 && xx < W) sum = fmaf(g[p * kD + o], __ldg(fpc + yy * feat.sh + xx * feat.sw), sum);
+            }
+        }
+        grad[((long long)b * C + c) * HW + (long long)y * W + x] = sum / fc;
+    }
+}
+
+static int check_corr_args(int B, int C, int H, int W) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return FLDR_ERR_INVALID_ARGUMENT;
+    if ((long long)H * W * 81 >= (1ll << 31) || B > 65535) return FLDR_ERR_UNSUPPORTED;
+    return FLDR_OK;
+}
+
+}  // namespace fldr
+
+using namespace fldr;
+
+extern "C" size_t fldr_corr81_fwd_workspace_bytes(int B, int C, int H, int W) {
+    (void)B; (void)C; (void)H; (void)W;
+    return 0;
+}
+
+extern "C" int fldr_corr81_fwd(const float* first, const int64_t* first_strides, const float* second,
+                               const int64_t* second_strides, float* out, int B, int C, int H, int W, void* ws,
+                               size_t ws_bytes, fldr_stream_t stream) {
+    (void)ws; (void)ws_bytes;
+    int st = check_corr_args(B, C, H, W);
+    if (st != FLDR_OK) return st;
+    if (!first || !second || !first_strides || !second_strides || !out) return FLDR_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    dim3 grid((W + fwd::TW - 1) / fwd::TW, (H + fwd::TH - 1) / fwd::TH, B);
+    corr81_fwd_kernel<<<grid, fwd::NT, 0, s>>>(make_view(first, first_strides), make_view(second, second_strides), out,
+                                              C, H, W);
+    return check_launch();
+}
+
+extern "C" size_t fldr_corr81_bwd_workspace_bytes(int B, int C, int H, int W) {
+    (void)B; (void)C; (void)H; (void)W;
+    return 0;
+}
+
+extern "C" int fldr_corr81_bwd(const float* first, const int64_t* first_strides, const float* second,
+                               const int64_t* second_strides, const float* grad_out, const int64_t* grad_out_strides,
+                               float* grad_first, float* grad_second, int B, int C, int H, int W, void* ws,
+                               size_t ws_bytes, fldr_stream_t stream) {
+    (void)ws; (void)ws_bytes;
+    int st = check_corr_args(B, C, H, W);
+    if (st != FLDR_OK) return st;
+    if (!first || !second || !first_strides || !second_strides || !grad_out || !grad_out_strides)
+        return FLDR_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int nchunks = (C + kBwdChunk - 1) / kBwdChunk;
+    const long long per_b = (long long)H * W * nchunks;
+    dim3 grid((unsigned)((per_b + 127) / 128), B, 1);
+    if (grad_first) {
+        corr81_bwd_kernel<false><<<grid, 128, 0, s>>>(make_view(second, second_strides),
+                                                      make_view(grad_out, grad_out_strides), grad_first, C, H, W, nchunks);
+        if ((st = check_launch()) != FLDR_OK) return st;
+    }
+    if (grad_second) {
+        corr81_bwd_kernel<true><<<grid, 128, 0, s>>>(make_view(first, first_strides),
+                                                     make_view(grad_out, grad_out_strides), grad_second, C, H, W, nchunks);
+        if ((st = check_launch()) != FLDR_OK) return st;
+    }
+    return FLDR_OK;
+}

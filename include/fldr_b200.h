@@ -1,0 +1,133 @@
+/*
+ * fldr_b200.h - C ABI of the B200-native (sm_100a) replacement for fLDR-VFI's two CuPy-JIT ops.
+ *
+ * Drop-in boundary.  Each entry point cites the reference interface it
+ * replaces (paths relative to the reference checkout):
+ *
+ *   fldr_splat_fwd   <- softSplat.py:320-352  FunctionSoftsplat(tenInput, tenFlow, tenMetric, strType)
+ *                       softSplat.py:222-259  _FunctionSoftsplat.forward + kernel_Softsplat_updateOutput (12-52)
+ *   fldr_splat_bwd   <- softSplat.py:262-317  _FunctionSoftsplat.backward + kernel_Softsplat_updateGradInput (54-98)
+ *                       + kernel_Softsplat_updateGradFlow (100-158), plus the autograd of the torch
+ *                       glue at 320-352 (metric / normaliser gradients)
+ *   fldr_corr81_fwd  <- OpticalFlow/correlation.py:296-348  _FunctionCorrelation.forward
+ *                       (kernel_Correlation_rearrange 17-42 x2 + kernel_Correlation_updateOutput 44-112)
+ *   fldr_corr81_bwd  <- OpticalFlow/correlation.py:353-409  _FunctionCorrelation.backward
+ *                       (kernel_Correlation_updateGradFirst 114-176, updateGradSecond 178-242)
+ *
+ * Conventions
+ *   - plain C: raw device pointers, explicit element strides, explicit sizes, a CUDA stream handle.
+ *   - all tensors are fp32 and live on the current CUDA device; nothing is allocated or freed here,
+ *     scratch comes from the caller (`ws`, size from the matching *_workspace_bytes call).
+ *   - every call is asynchronous on `stream`; no host synchronisation.
+ *   - return value: FLDR_OK (0) or a negative fldr_status.  No exceptions cross this boundary.
+ *   - strides are in ELEMENTS, for logical shape [N, C, H, W] (NCHW); outputs are written
+ *     NCHW-contiguous, exactly as the reference allocates them (softSplat.py:234, correlation.py:305).
+ */
+#ifndef FLDR_B200_H
+#define FLDR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLDR_B200_ABI_VERSION 1
+
+/* cudaStream_t without pulling CUDA headers into the consumer (cgo / JNI / ctypes friendly). */
+typedef struct CUstream_st* fldr_stream_t;
+
+typedef enum fldr_status {
+    FLDR_OK = 0,
+    FLDR_ERR_INVALID_ARGUMENT = -1,   /* null pointer, non-positive size, unknown mode, bad stride */
+    FLDR_ERR_WORKSPACE_TOO_SMALL = -2,
+    FLDR_ERR_CUDA = -3,               /* a CUDA runtime call failed; see fldr_last_cuda_error() */
+    FLDR_ERR_UNSUPPORTED = -4,        /* e.g. metric missing for 'linear' (softSplat.py:328) */
+    FLDR_ERR_NO_DEVICE = -5
+} fldr_status;
+
+/* strType of FunctionSoftsplat (softSplat.py:322) plus the raw summation splat of _FunctionSoftsplat. */
+typedef enum fldr_splat_mode {
+    FLDR_SPLAT_SUMMATION = 0,   /* y = (S - 0.5) * 2                      (softSplat.py:349 is unconditional) */
+    FLDR_SPLAT_AVERAGE = 1,     /* A = [x, 1]                             (325) */
+    FLDR_SPLAT_LINEAR = 2,      /* A = [x * z, z]        metric required  (328) */
+    FLDR_SPLAT_SOFTMAX = 3,     /* A = [(x+1)/2 * e^z, e^z]; metric NULL -> [(x+1)/2, 1]  (334-338) */
+    FLDR_SPLAT_RAW = 4          /* y = S : _FunctionSoftsplat.apply(input, flow), no pre/post-processing */
+} fldr_splat_mode;
+
+int fldr_abi_version(void);
+const char* fldr_status_string(int status);
+/* cudaError_t of the most recent failing CUDA call made by this library on the calling thread (0 if none). */
+int fldr_last_cuda_error(void);
+
+/* ---------------------------------------------------------------- splat ---------------------------------- */
+
+/* Scratch needed by fldr_splat_fwd for this shape (accumulator in pixel-interleaved layout). */
+size_t fldr_splat_fwd_workspace_bytes(int mode, int N, int C, int H, int W);
+
+/*
+ * Forward splat with the mode's pre/post-processing fused in.
+ *   in      [N,C,H,W]  strides in_strides[4]
+ *   flow    [N,2,H,W]  strides flow_strides[4]      (channel 0 = x displacement, 1 = y; softSplat.py:23-24)
+ *   metric  [N,1,H,W]  strides metric_strides[4], or NULL (allowed for SOFTMAX / AVERAGE / SUMMATION / RAW)
+ *   out     [N,C,H,W]  contiguous.  Holes (normaliser == 0) come out as -1 (softSplat.py:346-349).
+ *   norm    [N,1,H,W]  contiguous or NULL: raw normaliser S[:, C] before the 0 -> 1 fix-up, saved for
+ *                      fldr_splat_bwd.  Ignored (may be NULL) for SUMMATION / RAW.
+ * Pixels whose target coordinate is not finite are skipped (the reference device-asserts, 25-26).
+ */
+int fldr_splat_fwd(int mode,
+                   const float* in, const int64_t* in_strides,
+                   const float* flow, const int64_t* flow_strides,
+                   const float* metric, const int64_t* metric_strides,
+                   float* out, float* norm,
+                   int N, int C, int H, int W,
+                   void* ws, size_t ws_bytes, fldr_stream_t stream);
+
+size_t fldr_splat_bwd_workspace_bytes(int mode, int N, int C, int H, int W);
+
+/*
+ * Backward of fldr_splat_fwd.  Any of grad_in / grad_flow / grad_metric may be NULL (gradient not
+ * requested: softSplat.py:276-277 needs_input_grad).
+ *   out, norm   the forward results (contiguous); unused (may be NULL) for SUMMATION / RAW
+ *   grad_out    [N,C,H,W]  strides grad_out_strides[4]
+ *   grad_in     [N,C,H,W]  contiguous     grad_flow [N,2,H,W] contiguous     grad_metric [N,1,H,W] contiguous
+ */
+int fldr_splat_bwd(int mode,
+                   const float* in, const int64_t* in_strides,
+                   const float* flow, const int64_t* flow_strides,
+                   const float* metric, const int64_t* metric_strides,
+                   const float* out, const float* norm,
+                   const float* grad_out, const int64_t* grad_out_strides,
+                   float* grad_in, float* grad_flow, float* grad_metric,
+                   int N, int C, int H, int W,
+                   void* ws, size_t ws_bytes, fldr_stream_t stream);
+
+/* ------------------------------------------------------------ correlation -------------------------------- */
+
+size_t fldr_corr81_fwd_workspace_bytes(int B, int C, int H, int W);
+
+/*
+ * 81-channel cost volume, displacements dy,dx in [-4,4], zero padding, mean over channels:
+ *   out[b,(dy+4)*9+(dx+4),y,x] = (1/C) sum_c first[b,c,y,x] * second[b,c,y+dy,x+dx]
+ *   first, second [B,C,H,W] with strides; out [B,81,H,W] contiguous.
+ */
+int fldr_corr81_fwd(const float* first, const int64_t* first_strides,
+                    const float* second, const int64_t* second_strides,
+                    float* out, int B, int C, int H, int W,
+                    void* ws, size_t ws_bytes, fldr_stream_t stream);
+
+size_t fldr_corr81_bwd_workspace_bytes(int B, int C, int H, int W);
+
+/* grad_first / grad_second [B,C,H,W] contiguous, either may be NULL (correlation.py:358-361). */
+int fldr_corr81_bwd(const float* first, const int64_t* first_strides,
+                    const float* second, const int64_t* second_strides,
+                    const float* grad_out, const int64_t* grad_out_strides,
+                    float* grad_first, float* grad_second,
+                    int B, int C, int H, int W,
+                    void* ws, size_t ws_bytes, fldr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLDR_B200_H */

@@ -1,0 +1,80 @@
+"""Generate the golden fixtures in this directory from the REFERENCE'S OWN KERNEL TEXT.
+
+Run in the build container (needs /root/reference):  python tests/golden/make_golden.py
+
+Each ``*.npz`` holds seeded inputs and the outputs of the reference kernels executed on the
+host through ``oracle/_ref/libref_host.so`` (see oracle/build_ref.py).  Splat outputs depend
+on the atomic summation order; the host run is sequential-per-thread, so values are one
+valid order - consumers compare with the tolerances of BASELINE.json (1e-4 abs / 1e-5 rel),
+the correlation with 1e-5 relative to sum|f1*f2|/C.
+``wrapper_*`` entries went through ``FunctionSoftsplat``'s torch glue as RESTATED in
+oracle/splat_oracle.py (softSplat.py:320-352) around the reference kernels.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_host, synth  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def splat_case(name, N, C, H, W, regime, scale, seed):
+    x = synth.features(N, C, H, W, seed=seed)
+    fl = synth.flow(N, H, W, regime, seed=seed + 1) * scale
+    z = synth.metric(N, H, W, seed=seed + 2)
+    g = synth.grad((N, C, H, W), seed=seed + 3)
+    out = {"input": x, "flow": fl, "metric": z, "grad_out": g}
+    out["raw_out"] = ref_host.splat_update_output(x, fl)
+    out["raw_grad_input"] = ref_host.splat_update_grad_input(x, fl, g)
+    out["raw_grad_flow"] = ref_host.splat_update_grad_flow(x, fl, g)
+    for mode in ["summation", "average", "linear", "softmax"]:
+        xi = x.clone().requires_grad_(True)
+        fi = fl.clone().requires_grad_(True)
+        zi = z.clone().requires_grad_(True)
+        m = None if mode in ("summation", "average") else zi
+        y = ref_host.function_softsplat(xi, fi, m, mode)
+        wrt = [xi, fi] + ([zi] if m is not None else [])
+        grads = torch.autograd.grad(y, wrt, g)
+        out[f"wrapper_{mode}_out"] = y.detach()
+        out[f"wrapper_{mode}_grad_input"] = grads[0]
+        out[f"wrapper_{mode}_grad_flow"] = grads[1]
+        if m is not None:
+            out[f"wrapper_{mode}_grad_metric"] = grads[2]
+    # softmax with metric=None (feature-splat path, fLDRnet.py:386-387)
+    xi = x.clone().requires_grad_(True)
+    fi = fl.clone().requires_grad_(True)
+    y = ref_host.function_softsplat(xi, fi, None, "softmax")
+    gi, gf = torch.autograd.grad(y, [xi, fi], g)
+    out["wrapper_softmax_nometric_out"] = y.detach()
+    out["wrapper_softmax_nometric_grad_input"] = gi
+    out["wrapper_softmax_nometric_grad_flow"] = gf
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **{k: v.numpy() for k, v in out.items()})
+    print(name, {k: tuple(v.shape) for k, v in out.items() if k.startswith("raw")})
+
+
+def corr_case(name, B, C, H, W, seed):
+    f1 = synth.features(B, C, H, W, seed=seed)
+    f2 = synth.features(B, C, H, W, seed=seed + 1)
+    out = ref_host.corr_update_output(f1, f2)
+    g = synth.grad(tuple(out.shape), seed=seed + 2)
+    g1, g2 = ref_host.corr_update_grads(f1, f2, g)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), first=f1.numpy(), second=f2.numpy(), out=out.numpy(),
+                        grad_out=g.numpy(), grad_first=g1.numpy(), grad_second=g2.numpy(),
+                        rbot0=ref_host.corr_rearrange(f1).numpy())
+    print(name, tuple(out.shape))
+
+
+if __name__ == "__main__":
+    splat_case("splat_smooth", 2, 3, 24, 40, "F1", 40.0, 10)    # image-like C=3, smooth large flow
+    splat_case("splat_scatter", 1, 5, 17, 23, "F2", 1.0, 20)    # odd sizes, iid flow, C not multiple of 4
+    splat_case("splat_converge", 1, 3, 16, 24, "F3", 1.0, 30)   # max contention
+    splat_case("splat_border", 2, 4, 20, 32, "FB", 1.0, 40)     # ~25 % of targets out of frame
+    splat_case("splat_identity", 1, 3, 8, 12, "F0", 1.0, 50)    # zero flow
+    corr_case("corr_c40", 2, 40, 12, 20, 60)                    # C not multiple of 32
+    corr_case("corr_c32_odd", 1, 32, 9, 11, 70)                 # odd H, W
+    corr_case("corr_c196_tiny", 2, 196, 5, 8, 80)               # cfg2-literal level 6 shape

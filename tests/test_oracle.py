@@ -1,0 +1,136 @@
+"""CPU tests: the oracle restatement against (i) the golden vectors produced by the reference's own kernel
+text, (ii) that kernel text run live when oracle/_ref is available, (iii) analytic known-answer tests
+(SURVEY.md App. A.4 - ours, the reference ships none)."""
+import math
+
+import pytest
+import torch
+
+from oracle import corr_oracle as co
+from oracle import ref_host
+from oracle import splat_oracle as so
+from oracle import synth
+from util import assert_corr_close, assert_splat_close, load_golden
+
+SPLAT_CASES = ["splat_smooth", "splat_scatter", "splat_converge", "splat_border", "splat_identity"]
+CORR_CASES = ["corr_c40", "corr_c32_odd", "corr_c196_tiny"]
+
+
+@pytest.mark.parametrize("name", SPLAT_CASES)
+def test_splat_raw_vs_golden(name):
+    g = load_golden(name)
+    assert_splat_close(so.splat_raw(g["input"], g["flow"]), g["raw_out"], name + " raw fwd")
+    assert_splat_close(so.splat_raw_grad_input(g["flow"], g["grad_out"]), g["raw_grad_input"], name + " gradInput")
+    assert_splat_close(so.splat_raw_grad_flow(g["input"], g["flow"], g["grad_out"]), g["raw_grad_flow"], name + " gradFlow")
+
+
+@pytest.mark.parametrize("name", SPLAT_CASES)
+@pytest.mark.parametrize("mode", ["summation", "average", "linear", "softmax", "softmax_nometric"])
+def test_splat_wrapper_vs_golden(name, mode):
+    g = load_golden(name)
+    strType = "softmax" if mode == "softmax_nometric" else mode
+    metric = g["metric"] if mode in ("linear", "softmax") else None
+    y, gi, gf, gz = so.function_softsplat_grads(g["input"], g["flow"], metric, strType, g["grad_out"])
+    assert_splat_close(y, g[f"wrapper_{mode}_out"], f"{name} {mode} out")
+    assert_splat_close(gi, g[f"wrapper_{mode}_grad_input"], f"{name} {mode} grad_input")
+    assert_splat_close(gf, g[f"wrapper_{mode}_grad_flow"], f"{name} {mode} grad_flow")
+    if metric is not None:
+        assert_splat_close(gz, g[f"wrapper_{mode}_grad_metric"], f"{name} {mode} grad_metric")
+
+
+@pytest.mark.parametrize("name", CORR_CASES)
+def test_corr_vs_golden(name):
+    g = load_golden(name)
+    f1, f2 = g["first"], g["second"]
+    scale = co.correlation_fwd(f1.abs(), f2.abs())
+    assert_corr_close(co.correlation_fwd(f1, f2), g["out"], scale, name + " fwd")
+    gs = co.correlation_grad_first(f2.abs(), g["grad_out"].abs())
+    assert_corr_close(co.correlation_grad_first(f2, g["grad_out"]), g["grad_first"], gs, name + " gradFirst")
+    gs2 = co.correlation_grad_second(f1.abs(), g["grad_out"].abs())
+    assert_corr_close(co.correlation_grad_second(f1, g["grad_out"]), g["grad_second"], gs2, name + " gradSecond")
+    if "rbot0" in g:
+        assert torch.equal(co.rearrange(f1), g["rbot0"])
+
+
+@pytest.mark.skipif(not ref_host.available(), reason="oracle/_ref not built and /root/reference absent")
+def test_oracle_vs_reference_kernel_text_live():
+    """Fresh seeds (not in the fixtures): restatement vs the reference kernels executed on the host."""
+    x = synth.features(1, 6, 19, 27, seed=123)
+    fl = synth.flow(1, 19, 27, "F2", seed=124)
+    gout = synth.grad((1, 6, 19, 27), seed=125)
+    assert_splat_close(so.splat_raw(x, fl), ref_host.splat_update_output(x, fl), "live raw fwd")
+    assert_splat_close(so.splat_raw_grad_input(fl, gout), ref_host.splat_update_grad_input(x, fl, gout), "live gradInput")
+    assert_splat_close(so.splat_raw_grad_flow(x, fl, gout), ref_host.splat_update_grad_flow(x, fl, gout), "live gradFlow")
+    f1 = synth.features(1, 35, 7, 10, seed=126)
+    f2 = synth.features(1, 35, 7, 10, seed=127)
+    assert_corr_close(co.correlation_fwd(f1, f2), ref_host.corr_update_output(f1, f2),
+                      co.correlation_fwd(f1.abs(), f2.abs()), "live corr fwd")
+
+
+def test_explicit_backward_matches_autograd_fp64():
+    """The explicit gradInput / gradFlow restatements equal autograd of the fp64 forward (floor is constant)."""
+    x = synth.features(1, 3, 10, 14, seed=5).double()
+    fl = (synth.flow(1, 10, 14, "F2", seed=6)).double()
+    g = synth.grad((1, 3, 10, 14), seed=7).double()
+    xr = x.clone().requires_grad_(True)
+    fr = fl.clone().requires_grad_(True)
+    N, C, H, W = x.shape
+    X, Y, x0, y0 = so._corners(fr)
+    out = torch.zeros(N, C, H * W, dtype=torch.float64)
+    for dx, dy, w in so._weights(X, Y, x0, y0):
+        cx, cy = x0.long() + dx, y0.long() + dy
+        valid = ((cx >= 0) & (cx < W) & (cy >= 0) & (cy < H)).reshape(N, 1, H * W)
+        idx = (cy.clamp(0, H - 1) * W + cx.clamp(0, W - 1)).reshape(N, 1, H * W).expand(N, C, H * W)
+        out = out.scatter_add(2, idx, torch.where(valid, xr.reshape(N, C, H * W) * w.reshape(N, 1, H * W), torch.zeros((), dtype=torch.float64)))
+    gi, gf = torch.autograd.grad(out.reshape(N, C, H, W), [xr, fr], g)
+    assert torch.allclose(gi, so.splat_raw_grad_input(fl, g), atol=1e-12)
+    assert torch.allclose(gf, so.splat_raw_grad_flow(x, fl, g), atol=1e-12)
+
+
+# ------------------------------------------------------------------ known-answer tests (App. A.4)
+def test_kat_zero_flow_identity():
+    x = synth.image(1, 3, 12, 16, seed=1)
+    fl = torch.zeros(1, 2, 12, 16)
+    z = synth.metric(1, 12, 16)
+    assert torch.allclose(so.function_softsplat(x, fl, z, "softmax"), x, atol=1e-6)
+    assert torch.allclose(so.function_softsplat(x, fl, None, "softmax"), x, atol=1e-6)
+    assert torch.allclose(so.function_softsplat(x, fl, None, "summation"), (x - 0.5) * 2, atol=1e-6)
+
+
+def test_kat_integer_shift_and_holes():
+    x = synth.image(1, 3, 10, 12, seed=2)
+    fl = torch.zeros(1, 2, 10, 12)
+    fl[:, 0] = 3.0
+    fl[:, 1] = -2.0
+    y = so.function_softsplat(x, fl, None, "softmax")
+    assert torch.allclose(y[:, :, :8, 3:], x[:, :, 2:, :9], atol=1e-6)
+    assert bool((y[:, :, 8:, :] == -1).all()) and bool((y[:, :, :, :3] == -1).all())   # vacated pixels are holes -> -1
+
+
+def test_kat_half_pixel_box_and_weighted_mean():
+    x = synth.image(1, 1, 4, 8, seed=3)
+    fl = torch.zeros(1, 2, 4, 8)
+    fl[:, 0] = 0.5
+    z = torch.full((1, 1, 4, 8), -0.7)
+    y = so.function_softsplat(x, fl, z, "softmax")
+    assert torch.allclose(y[:, :, :, 1:], 0.5 * (x[:, :, :, 1:] + x[:, :, :, :-1]), atol=1e-6)
+    # two sources onto one target with z = (0, ln 3) -> 1:3 weighted mean
+    x2 = torch.tensor([0.2, -0.6]).view(1, 1, 1, 2)
+    f2 = torch.zeros(1, 2, 1, 2)
+    f2[0, 0, 0, 1] = -1.0
+    z2 = torch.tensor([0.0, math.log(3.0)]).view(1, 1, 1, 2)
+    y2 = so.function_softsplat(x2, f2, z2, "softmax")
+    assert abs(float(y2[0, 0, 0, 0]) - (0.25 * 0.2 + 0.75 * -0.6)) < 1e-6
+    assert float(y2[0, 0, 0, 1]) == -1.0
+
+
+def test_kat_correlation():
+    f = synth.features(1, 8, 12, 14, seed=4)
+    out = co.correlation_fwd(f, f)
+    assert torch.allclose(out[:, 40], (f * f).mean(1), atol=1e-6)
+    sh = torch.roll(f, shifts=(2, -3), dims=(2, 3))      # f2[y, x] = f[y-2, x+3]  -> f2[y+2, x-3] = f[y, x]
+    out2 = co.correlation_fwd(f, sh)
+    ch = (2 + 4) * 9 + (-3 + 4)
+    assert torch.allclose(out2[:, ch, 4:-4, 4:-4], (f * f).mean(1)[:, 4:-4, 4:-4], atol=1e-6)
+    # the 4-pixel border ring sees zero padding: displacement (-4,-4) at pixel (0,0) reads outside the frame
+    assert float(out[0, 0, 0, 0]) == 0.0
