@@ -1,0 +1,104 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU and exports every symbol that
+include/fldr_b200.h declares; argument validation that needs no device; host-mirror error behaviour."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    sys.path.insert(0, os.path.join(ROOT, "fldr-vfi_b200"))
+    import build as fldr_build
+    sys.path.pop(0)
+    fldr_build.build(verbose=False)
+    import fldr_vfi_b200._lib as L
+    return L.lib()
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fldr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fldr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    import fldr_vfi_b200._lib as L
+    names = _declared_symbols()
+    assert len(names) >= 11
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/fldr_b200.h but not exported"
+    assert sorted(L.SYMBOLS) == names, "ctypes binding table and header disagree"
+
+
+def test_status_strings_and_version(lib):
+    assert lib.fldr_abi_version() == 1
+    assert lib.fldr_status_string(0) == b"FLDR_OK"
+    for code in (-1, -2, -3, -4, -5):
+        assert lib.fldr_status_string(code).startswith(b"FLDR_ERR_")
+    assert lib.fldr_status_string(-99) == b"FLDR_ERR_UNKNOWN"
+
+
+def test_workspace_sizes(lib):
+    # pixel-interleaved accumulator: N*H*W*round_up(C+1,4) floats
+    assert lib.fldr_splat_fwd_workspace_bytes(3, 1, 3, 2304, 4096) == 2304 * 4096 * 4 * 4
+    assert lib.fldr_splat_fwd_workspace_bytes(3, 1, 48, 288, 512) == 288 * 512 * 52 * 4
+    assert lib.fldr_splat_fwd_workspace_bytes(4, 2, 5, 7, 9) == (2 * 7 * 9 * 8 * 4 + 255) // 256 * 256
+    assert lib.fldr_splat_fwd_workspace_bytes(9, 1, 3, 8, 8) == 0          # unknown mode
+
+
+def test_argument_validation_needs_no_device(lib):
+    s4 = (ctypes.c_int64 * 4)(0, 0, 0, 0)
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    # null input
+    assert lib.fldr_splat_fwd(3, None, s4, p, s4, None, None, p, None, 1, 3, 8, 8, p, 1 << 20, None) == -1
+    # unknown mode / bad sizes
+    assert lib.fldr_splat_fwd(7, p, s4, p, s4, None, None, p, None, 1, 3, 8, 8, p, 1 << 20, None) == -1
+    assert lib.fldr_splat_fwd(3, p, s4, p, s4, None, None, p, None, 1, 0, 8, 8, p, 1 << 20, None) == -1
+    # linear without metric (softSplat.py:328)
+    assert lib.fldr_splat_fwd(2, p, s4, p, s4, None, None, p, None, 1, 3, 8, 8, p, 1 << 20, None) == -4
+    # workspace too small
+    assert lib.fldr_splat_fwd(3, p, s4, p, s4, None, None, p, None, 1, 3, 8, 8, p, 16, None) == -2
+    assert lib.fldr_corr81_fwd(None, s4, p, s4, p, 1, 4, 8, 8, None, 0, None) == -1
+    assert lib.fldr_corr81_fwd(p, s4, p, s4, p, 0, 4, 8, 8, None, 0, None) == -1
+    assert lib.fldr_corr81_bwd(p, s4, p, s4, None, s4, p, p, 1, 4, 8, 8, None, 0, None) == -1
+
+
+def test_host_mirror_names_and_cpu_errors(lib):
+    import fldr_vfi_b200.correlation as C
+    import fldr_vfi_b200.softSplat as S
+    for name in ("Softsplat", "FunctionSoftsplat", "_FunctionSoftsplat"):
+        assert hasattr(S, name)
+    for name in ("ModuleCorrelation", "FunctionCorrelation", "_FunctionCorrelation"):
+        assert hasattr(C, name)
+    assert S.Softsplat().strType == "softmax"                     # softSplat.py:356
+    x, fl = torch.zeros(1, 3, 4, 4), torch.zeros(1, 2, 4, 4)
+    with pytest.raises(NotImplementedError):                      # no CPU path, no fallback (softSplat.py:251-252)
+        S.Softsplat()(x, fl)
+    with pytest.raises(NotImplementedError):                      # correlation.py:343-344
+        C.FunctionCorrelation(tensorFirst=x, tensorSecond=x)
+    with pytest.raises(AssertionError):
+        S.FunctionSoftsplat(x, fl, None, "nearest")
+
+
+def test_dropin_import_names_shadow_reference_modules(lib):
+    """`from softSplat import Softsplat` (fLDRnet.py:22) and `from . import correlation` inside the OpticalFlow
+    namespace package (PWCNet.py:4) resolve to the drop-ins when dropin/ is first on sys.path.  Importing the
+    correlation drop-in must not touch CUDA (the reference does at correlation.py:7-8)."""
+    import subprocess
+    code = (
+        "import sys; sys.path.insert(0, r'%s');"
+        "import softSplat, OpticalFlow.correlation as oc;"
+        "assert 'dropin' in softSplat.__file__ and 'dropin' in oc.__file__;"
+        "assert softSplat.Softsplat.__module__ == 'fldr_vfi_b200.softSplat';"
+        "assert oc.FunctionCorrelation.__module__ == 'fldr_vfi_b200.correlation';"
+        "print('ok')" % os.path.join(ROOT, "fldr-vfi_b200", "dropin"))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
+    assert res.returncode == 0 and "ok" in res.stdout, res.stderr

@@ -1,0 +1,95 @@
+"""GPU parity tests for the 81-channel correlation: CUDA path (through the C-ABI) vs the CPU oracle, the golden
+vectors of the reference kernel text, PWC pyramid shapes, and properties at the native 4K size."""
+import pytest
+import torch
+
+from oracle import corr_oracle as co
+from oracle import synth
+from util import assert_corr_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+CORR_CASES = ["corr_c40", "corr_c32_odd", "corr_c196_tiny"]
+
+
+def _mod(cuda_lib):
+    import fldr_vfi_b200.correlation as C
+    return C
+
+
+def _check(Cm, f1, f2, gout, what):
+    f1d = f1.cuda().requires_grad_(True)
+    f2d = f2.cuda().requires_grad_(True)
+    out = Cm.FunctionCorrelation(tensorFirst=f1d, tensorSecond=f2d)
+    assert out.shape == (f1.shape[0], 81, f1.shape[2], f1.shape[3]) and out.is_contiguous()
+    assert_corr_close(out, co.correlation_fwd(f1, f2), co.correlation_fwd(f1.abs(), f2.abs()), what + " fwd")
+    g1, g2 = torch.autograd.grad(out, [f1d, f2d], gout.cuda())
+    assert_corr_close(g1, co.correlation_grad_first(f2, gout), co.correlation_grad_first(f2.abs(), gout.abs()), what + " gradFirst")
+    assert_corr_close(g2, co.correlation_grad_second(f1, gout), co.correlation_grad_second(f1.abs(), gout.abs()), what + " gradSecond")
+
+
+@pytest.mark.parametrize("name", CORR_CASES)
+def test_vs_golden(cuda_lib, name):
+    Cm = _mod(cuda_lib)
+    g = load_golden(name)
+    f1, f2 = g["first"], g["second"]
+    f1d = f1.cuda().requires_grad_(True)
+    f2d = f2.cuda().requires_grad_(True)
+    out = Cm.ModuleCorrelation()(f1d, f2d)
+    assert_corr_close(out, g["out"], co.correlation_fwd(f1.abs(), f2.abs()), name + " fwd")
+    g1, g2 = torch.autograd.grad(out, [f1d, f2d], g["grad_out"].cuda())
+    assert_corr_close(g1, g["grad_first"], co.correlation_grad_first(f2.abs(), g["grad_out"].abs()), name + " gradFirst")
+    assert_corr_close(g2, g["grad_second"], co.correlation_grad_second(f1.abs(), g["grad_out"].abs()), name + " gradSecond")
+
+
+# cfg2 literal pyramid (4K / 8 -> 320x512, B=2) and ragged shapes
+@pytest.mark.parametrize("B,C,H,W", [
+    (2, 196, 5, 8), (2, 128, 10, 16), (2, 96, 20, 32), (2, 64, 40, 64), (2, 32, 80, 128),
+    (1, 1, 1, 1), (1, 3, 9, 7), (2, 17, 13, 37), (1, 33, 8, 70),
+])
+def test_vs_oracle_seeded(cuda_lib, B, C, H, W):
+    Cm = _mod(cuda_lib)
+    f1 = synth.features(B, C, H, W, seed=3)
+    f2 = synth.features(B, C, H, W, seed=5)
+    gout = synth.grad((B, 81, H, W), seed=4)
+    _check(Cm, f1, f2, gout, f"B{B} C{C} {H}x{W}")
+
+
+def test_needs_input_grad(cuda_lib):
+    Cm = _mod(cuda_lib)
+    f1 = synth.features(1, 16, 12, 12, seed=1).cuda().requires_grad_(True)
+    f2 = synth.features(1, 16, 12, 12, seed=2).cuda()
+    out = Cm.FunctionCorrelation(f1, f2)
+    out.sum().backward()
+    assert f1.grad is not None and f2.grad is None
+
+
+def test_error_behaviour(cuda_lib):
+    Cm = _mod(cuda_lib)
+    f = torch.zeros(1, 4, 8, 8)
+    with pytest.raises(NotImplementedError):
+        Cm.FunctionCorrelation(f, f)                                       # correlation.py:343-344
+    with pytest.raises(AssertionError):
+        Cm.FunctionCorrelation(f.cuda().permute(0, 1, 3, 2), f.cuda())    # correlation.py:302
+    with pytest.raises(TypeError):
+        Cm.FunctionCorrelation(f.cuda().double(), f.cuda().double())
+
+
+def test_native_4k_level_properties_and_crop(cuda_lib):
+    """cfg2-native level 2 (B=2, C=32, 544x1024): f1==f2 -> centre channel = mean f1^2; swap symmetry; the oracle at full size (~3 s)."""
+    Cm = _mod(cuda_lib)
+    B, C, H, W = 2, 32, 544, 1024
+    f1 = synth.features(B, C, H, W, seed=61)
+    f2 = synth.features(B, C, H, W, seed=62)
+    f1d, f2d = f1.cuda(), f2.cuda()
+    same = Cm.FunctionCorrelation(f1d, f1d)
+    assert float((same[:, 40] - (f1d * f1d).mean(1)).abs().max()) <= 1e-5
+    a = Cm.FunctionCorrelation(f1d, f2d)
+    bsw = Cm.FunctionCorrelation(f2d, f1d)
+    # corr(f1,f2)[dy,dx](y,x) == corr(f2,f1)[-dy,-dx](y+dy,x+dx)
+    for (dy, dx) in ((-4, -4), (0, 3), (2, -1), (4, 4)):
+        ch, chm = (dy + 4) * 9 + dx + 4, (-dy + 4) * 9 - dx + 4
+        ya, xa = slice(max(0, -dy), H - max(0, dy)), slice(max(0, -dx), W - max(0, dx))
+        yb, xb = slice(max(0, dy), H - max(0, -dy)), slice(max(0, dx), W - max(0, -dx))
+        assert float((a[:, ch, ya, xa] - bsw[:, chm, yb, xb]).abs().max()) <= 2e-6
+    assert_corr_close(a, co.correlation_fwd(f1, f2), co.correlation_fwd(f1.abs(), f2.abs()), "native level 2 vs oracle")
