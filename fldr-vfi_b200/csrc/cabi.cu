@@ -36,3 +36,44 @@ extern "C" const char* fldr_status_string(int status) {
         default: return "FLDR_ERR_UNKNOWN";
     }
 }
+
+// ---- TMA tensor-map encoding through the runtime's driver entry point (no -lcuda at link time) ----
+#include "tma.cuh"
+
+namespace fldr {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+bool encode_tensor_map_4d(CUtensorMap* map, const float* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                          const uint32_t box[4]) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+    for (int i = 0; i < 3; ++i)
+        if ((strides_bytes[i] & 15) != 0 || strides_bytes[i] >= (1ull << 40)) return false;
+    for (int i = 0; i < 4; ++i)
+        if (box[i] == 0 || box[i] > 256) return false;
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+}  // namespace fldr

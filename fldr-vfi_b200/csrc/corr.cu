@@ -4,6 +4,7 @@
 // launched once per sample).  No NHWC scratch copies: tiles of the NCHW inputs are staged in shared memory
 // with their 4-pixel halo and zero fill, and every thread register-blocks 4 pixels x 3 dy x 9 dx.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace fldr {
 
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(fwd::NT) corr81_fwd_kernel(View4 f1, View4 f2,
 
     const int y = y0t + row, x = x0t + pg * 4;
     if (y >= H || x >= W) return;
-    const float fc = (float)C;
+    const float rc = 1.0f / (float)C;   // sum * (1/C): within 1 ulp of the reference's sum / C (exact for power-of-two C)
     const long long HW = (long long)H * W;
     float* ob = out + (long long)b * 81 * HW + (long long)y * W + x;
     const bool vec = ((W & 3) == 0) && (x + 3 < W);
@@ -86,13 +87,155 @@ __global__ void __launch_bounds__(fwd::NT) corr81_fwd_kernel(View4 f1, View4 f2,
             float* op = ob + (long long)((dyg * 3 + d) * kD + o) * HW;
             if (vec) {
                 *reinterpret_cast<float4*>(op) =
-                    make_float4(acc[d][o][0] / fc, acc[d][o][1] / fc, acc[d][o][2] / fc, acc[d][o][3] / fc);
+                    make_float4(acc[d][o][0] * rc, acc[d][o][1] * rc, acc[d][o][2] * rc, acc[d][o][3] * rc);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (x + j < W) op[j] = acc[d][o][j] / fc;
+                    if (x + j < W) op[j] = acc[d][o][j] * rc;
             }
         }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward, TMA path (W % 4 == 0, 16-byte aligned rows): persistent CTAs, one per SM, loop over 32 x TH output
+// tiles.  Per tile and chunk of CK channels two TMA boxes land in shared memory - first[CK][TH][32] and
+// second[CK][TH+8][40] with its 4-pixel halo; out-of-frame rows/columns/channels are zero-filled by the TMA
+// unit, which IS the reference's zero padding (correlation.py:297-298 + rearrange) at no cost.  A 3-stage
+// full/empty mbarrier ring keeps the loads STAGES-1 chunks ahead of the FFMA loop, across tile boundaries.
+// ------------------------------------------------------------------------------------------------
+namespace fwdtma {
+constexpr int TW = 32, CK = 8, STAGES = 3;
+template <int TH> struct Cfg {
+    static constexpr int NT = 8 * TH * 3;
+    static constexpr int F2H = TH + 2 * kPad, F2W = TW + 2 * kPad;
+    static constexpr int S1 = CK * TH * TW, S2 = CK * F2H * F2W;       // floats
+    static constexpr int STAGE_BYTES = (S1 + S2) * 4;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8;
+};
+}  // namespace fwdtma
+
+template <int TH>
+__global__ void __launch_bounds__(fwdtma::Cfg<TH>::NT, TH == 8 ? 2 : 1)
+corr81_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
+                      float* __restrict__ out, int B, int C, int H, int W, int tilesX, int tilesY) {
+    using namespace fwdtma;
+    using K = Cfg<TH>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * K::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    const int tid = threadIdx.x;
+    const int pg = tid & 7, row = (tid >> 3) % TH, dyg = tid / (8 * TH);
+    constexpr int NWARPS = K::NT / 32;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWARPS); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tm1);
+        tma_prefetch_desc(&tm2);
+    }
+    __syncthreads();
+
+    const int nchunks = (C + CK - 1) / CK;
+    const int ntiles = tilesX * tilesY * B;
+    const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const long long total = (long long)my_tiles * nchunks;
+
+    auto issue = [&](long long g) {     // thread 0 only
+        const int tl = (int)(g / nchunks), ch = (int)(g % nchunks);
+        const int tile = blockIdx.x + tl * gridDim.x;
+        const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, b = tile / (tilesX * tilesY);
+        const int st = (int)(g % STAGES);
+        if (g >= STAGES) mbar_wait(&empty[st], (uint32_t)((g / STAGES - 1) & 1));
+        float* s1 = reinterpret_cast<float*>(smem_raw + st * K::STAGE_BYTES);
+        float* s2 = s1 + K::S1;
+        mbar_arrive_expect_tx(&full[st], K::STAGE_BYTES);
+        tma_load_4d(s1, &tm1, &full[st], tx * TW, ty * TH, ch * CK, b);
+        tma_load_4d(s2, &tm2, &full[st], tx * TW - kPad, ty * TH - kPad, ch * CK, b);
+    };
+
+    long long prod = 0;
+    if (tid == 0)
+        for (; prod < total && prod < STAGES - 1; ++prod) issue(prod);
+
+    const float rc = 1.0f / (float)C;
+    const long long HW = (long long)H * W;
+    long long g = 0;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+        float acc[3][kD][4];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int o = 0; o < kD; ++o)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[d][o][j] = 0.f;
+
+        for (int ch = 0; ch < nchunks; ++ch, ++g) {
+            if (tid == 0 && prod < total) { issue(prod); ++prod; }
+            const int st = (int)(g % STAGES);
+            mbar_wait(&full[st], (uint32_t)((g / STAGES) & 1));
+            const float* s1 = reinterpret_cast<const float*>(smem_raw + st * K::STAGE_BYTES);
+            const float* s2 = s1 + K::S1;
+            const float* p1 = s1 + row * TW + pg * 4;
+            const float* p2 = s2 + (row + dyg * 3) * K::F2W + pg * 4;
+#pragma unroll 2
+            for (int c = 0; c < CK; ++c) {
+                const float4 a4 = *reinterpret_cast<const float4*>(p1 + c * (TH * TW));
+                const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const float4* rp = reinterpret_cast<const float4*>(p2 + c * (K::F2H * K::F2W) + d * K::F2W);
+                    const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
+                    const float f[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+                    for (int o = 0; o < kD; ++o)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[d][o][j] = fmaf(a[j], f[j + o], acc[d][o][j]);
+                }
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+        }
+
+        const int tile = blockIdx.x + tl * gridDim.x;
+        const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, b = tile / (tilesX * tilesY);
+        const int y = ty * TH + row, x = tx * TW + pg * 4;
+        if (y < H && x < W) {      // W % 4 == 0 on this path: the 4-pixel group is all in or all out
+            float* ob = out + (long long)b * 81 * HW + (long long)y * W + x;
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int o = 0; o < kD; ++o)
+                    __stcs(reinterpret_cast<float4*>(ob + (long long)((dyg * 3 + d) * kD + o) * HW),
+                           make_float4(acc[d][o][0] * rc, acc[d][o][1] * rc, acc[d][o][2] * rc, acc[d][o][3] * rc));
+        }
+    }
+}
+
+template <int TH>
+static int launch_fwd_tma(const View4& f1, const View4& f2, float* out, int B, int C, int H, int W, cudaStream_t s,
+                          bool* used) {
+    using namespace fwdtma;
+    using K = Cfg<TH>;
+    *used = false;
+    CUtensorMap tm1, tm2;
+    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)B};
+    const uint64_t st1[3] = {(uint64_t)f1.sh * 4, (uint64_t)f1.sc * 4, (uint64_t)f1.sn * 4};
+    const uint64_t st2[3] = {(uint64_t)f2.sh * 4, (uint64_t)f2.sc * 4, (uint64_t)f2.sn * 4};
+    const uint32_t box1[4] = {TW, TH, CK, 1};
+    const uint32_t box2[4] = {(uint32_t)K::F2W, (uint32_t)K::F2H, CK, 1};
+    if (!encode_tensor_map_4d(&tm1, f1.p, dims, st1, box1) || !encode_tensor_map_4d(&tm2, f2.p, dims, st2, box2))
+        return FLDR_OK;   // not describable: caller falls back to the generic kernel
+    {   // per device, cheap: raise the dynamic shared memory limit every launch (one process may drive several GPUs)
+        cudaError_t e = cudaFuncSetAttribute(corr81_fwd_tma_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
+    }
+    const int tilesX = (W + TW - 1) / TW, tilesY = (H + TH - 1) / TH;
+    const int ntiles = tilesX * tilesY * B;
+    const int per_sm = (TH == 8) ? 2 : 1;
+    const int grid = ntiles < sm_count() * per_sm ? ntiles : sm_count() * per_sm;
+    corr81_fwd_tma_kernel<TH><<<grid, K::NT, K::SMEM_BYTES, s>>>(tm1, tm2, out, B, C, H, W, tilesX, tilesY);
+    *used = true;
+    return check_launch();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -171,9 +314,19 @@ extern "C" int fldr_corr81_fwd(const float* first, const int64_t* first_strides,
     if (st != FLDR_OK) return st;
     if (!first || !second || !first_strides || !second_strides || !out) return FLDR_ERR_INVALID_ARGUMENT;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const View4 v1 = make_view(first, first_strides), v2 = make_view(second, second_strides);
+    // TMA path: unit inner stride, rows 16-byte aligned, strides positive (views with stride 0 / negative fall back)
+    const bool tma_ok = (W % 4 == 0) && v1.sw == 1 && v2.sw == 1 && v1.sh > 0 && v1.sc > 0 && v2.sh > 0 && v2.sc > 0 &&
+                        (B == 1 || (v1.sn > 0 && v2.sn > 0));
+    if (tma_ok) {
+        bool used = false;
+        const long long tiles16 = (long long)((W + 31) / 32) * ((H + 15) / 16) * B;
+        st = (tiles16 >= 2ll * sm_count()) ? launch_fwd_tma<16>(v1, v2, out, B, C, H, W, s, &used)
+                                           : launch_fwd_tma<8>(v1, v2, out, B, C, H, W, s, &used);
+        if (st != FLDR_OK || used) return st;
+    }
     dim3 grid((W + fwd::TW - 1) / fwd::TW, (H + fwd::TH - 1) / fwd::TH, B);
-    corr81_fwd_kernel<<<grid, fwd::NT, 0, s>>>(make_view(first, first_strides), make_view(second, second_strides), out,
-                                              C, H, W);
+    corr81_fwd_kernel<<<grid, fwd::NT, 0, s>>>(v1, v2, out, C, H, W);
     return check_launch();
 }
 
