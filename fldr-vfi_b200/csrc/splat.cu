@@ -11,6 +11,7 @@
 //               of CP scalar REDs to CP planes (the reference issues 4 scalar REDs per element, 39-50).
 //   outputs     NCHW contiguous (what the reference allocates, softSplat.py:234).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -68,88 +69,192 @@ __device__ __forceinline__ float source_weight(const SplatGeom& g, const View4& 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pass 1: scatter.  One thread per source pixel, lanes along x (coalesced plane reads; neighbouring lanes
-// hit neighbouring accumulator pixels for smooth flow).
+// Pass 1: scatter with merged reductions.
+//
+// Measured on B200 (profiles/r1_microbench_design.txt): the L2 reduction unit sustains ~333 G 16-byte REDs/s for
+// coalesced targets (113 us for the 4 REDs/pixel of one 4K image), ~81 G/s for random targets, and shared-memory
+// atomics are slower still (226 us) - so the lever is issuing FEWER reductions, not privatising them.
+// A thread owns one column and walks R source rows; lanes of a warp own adjacent columns.  Wherever the flow is
+// locally constant
+//   * the NE/SE contribution of column x lands on the pixel that column x+1 hits with NW/SW -> handed to the right
+//     lane by warp shuffle, and
+//   * the SW/SE contribution of row y lands on the pixel that row y+1 hits with NW/NE       -> carried in registers
+// so a source pixel costs ~1 red.global.add.v4.f32 instead of 4 (the reference issues 4 scalar REDs per ELEMENT,
+// softSplat.py:39-50).  A target mismatch simply flushes the carried value as its own RED: arbitrary flow stays
+// correct, it only merges less.  Inactive pixels (out of frame, non-finite) carry sentinel coordinates that never match
+// and never pass the frame test, so no per-corner flags are kept.
+// Accumulator layout: [N][Q][H][W][4] fp32, Q = ceil(CA/4): every channel quad is a pixel-interleaved float4 image,
+// so lanes (adjacent x) reduce into adjacent 16-byte slots.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) splat_scatter_kernel(View4 in, View4 flow, View4 metric,
-                                                            float* __restrict__ acc, SplatGeom g) {
-    const long long HW = (long long)g.H * g.W;
-    const long long total = HW * g.N;
-    const bool pre = g.mode == FLDR_SPLAT_SOFTMAX;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % g.W);
-        const int y = (int)((idx / g.W) % g.H);
-        const int n = (int)(idx / HW);
-        const float* fp = flow.p + n * flow.sn + y * flow.sh + x * flow.sw;
-        Corners k;
-        if (!make_corners(x, y, __ldg(fp), __ldg(fp + flow.sc), g.W, g.H, k)) continue;
-        const float m = source_weight(g, metric, n, y, x);
-        float* accn = acc + (long long)n * HW * g.CP;
-        float* dst[4];
-        dst[0] = accn + ((long long)k.y0 * g.W + k.x0) * g.CP;
-        dst[1] = dst[0] + g.CP;
-        dst[2] = dst[0] + (long long)g.W * g.CP;
-        dst[3] = dst[2] + g.CP;
-        const float* ip = in.p + n * in.sn + y * in.sh + x * in.sw;
-        for (int q = 0; q < g.CP; q += 4) {
-            float a[4];
+constexpr int kSentinel = -(1 << 28);
+
+template <int PX> __device__ __forceinline__ void vstore(float* p, const float* t);
+template <> __device__ __forceinline__ void vstore<1>(float* p, const float* t) { __stcs(p, t[0]); }
+template <> __device__ __forceinline__ void vstore<4>(float* p, const float* t) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(t[0], t[1], t[2], t[3]));
+}
+
+// WKIND: 0 = weight 1 (no metric / average / summation / raw), 1 = exp(z) (softmax), 2 = z (linear)
+template <int R, int WKIND, bool PRE>
+__global__ void __launch_bounds__(128) splat_scatter_merged_kernel(View4 in, View4 flow, View4 metric,
+                                                                   float* __restrict__ acc, SplatGeom g, int Q) {
+    const int lane = threadIdx.x & 31;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yb = blockIdx.y * R;
+    const int q = blockIdx.z % Q, n = blockIdx.z / Q;
+    const int W = g.W, H = g.H;
+    const bool inb = x < W;
+    float4* accq = reinterpret_cast<float4*>(acc) + (long long)(n * Q + q) * H * W;
+    const int rows = min(R, H - yb);
+
+    // per-tensor element offsets of (n, *, yb, x); advanced by the row stride each iteration
+    const float* fu = flow.p + n * flow.sn + (long long)yb * flow.sh + (long long)x * flow.sw;
+    const float* fv = fu + flow.sc;
+    const float* zp = WKIND ? metric.p + n * metric.sn + (long long)yb * metric.sh + (long long)x * metric.sw : nullptr;
+    const float* ip = in.p + n * in.sn + (long long)(q * 4) * in.sc + (long long)yb * in.sh + (long long)x * in.sw;
+    const int nch = min(4, g.C - q * 4);                 // real channels in this quad (<= 0: only the weight slot)
+    const int wslot = (g.CA > g.C) ? g.C - q * 4 : -1;    // slot of this quad that carries the weight, if in [0,4)
+    const float xf = (float)x;
+
+    float pw[4] = {0.f, 0.f, 0.f, 0.f}, pe[4] = {0.f, 0.f, 0.f, 0.f};
+    int px = kSentinel, pex = kSentinel, py = kSentinel;
+
+    // software pipeline: the loads of row r+1 are issued before row r is processed
+    float nu = 0.f, nv = 0.f, nz = 0.f, nx[4] = {0.f, 0.f, 0.f, 0.f};
+    auto load = [&](int r) {
+        if (inb) {
+            nu = __ldg(fu + (long long)r * flow.sh);
+            nv = __ldg(fv + (long long)r * flow.sh);
+            if (WKIND) nz = __ldg(zp + (long long)r * metric.sh);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < nch) nx[j] = __ldg(ip + (long long)j * in.sc + (long long)r * in.sh);
+        }
+    };
+    if (rows > 0) load(0);
+
+#pragma unroll 2
+    for (int r = 0; r < rows; ++r) {
+        const float u = nu, v = nv, z = nz;
+        const float xv[4] = {nx[0], nx[1], nx[2], nx[3]};
+        if (r + 1 < rows) load(r + 1);
+
+        // softSplat.py:23-38
+        const float X = xf + u, Y = (float)(yb + r) + v;
+        const float fx0 = floorf(X), fy0 = floorf(Y);
+        const bool ok = inb && fx0 >= -1.f && fx0 < (float)W && fy0 >= -1.f && fy0 < (float)H;   // false for NaN / inf
+        const int x0 = ok ? (int)fx0 : kSentinel;
+        const int y0 = ok ? (int)fy0 : kSentinel;
+        const float ax = (fx0 + 1.f) - X, bx = X - fx0, ay = (fy0 + 1.f) - Y, by = Y - fy0;
+        const float wNW = ax * ay, wNE = bx * ay, wSW = ax * by, wSE = bx * by;
+        float m = 1.f;
+        if (WKIND == 1) m = expf(z);          // accurate expf: the parity bar is 1e-5 relative
+        if (WKIND == 2) m = z;
+        float tW[4], tE[4], bW[4], bE[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a = xv[j];
+            if (PRE) a = (a + 1.f) * 0.5f;                      // softSplat.py:334
+            a = (j < nch) ? a * m : (j == wslot ? m : 0.f);     // softSplat.py:328 / 338, weight slot, padding
+            if (!ok) a = 0.f;
+            tW[j] = a * wNW; tE[j] = a * wNE; bW[j] = a * wSW; bE[j] = a * wSE;
+        }
+
+        // vertical: the previous row's bottom contributions join this row's top ones when they hit the same pixels
+        if (x0 == px && y0 == py) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { tW[j] += pw[j]; tE[j] += pe[j]; }
+        } else {
+            if ((unsigned)py < (unsigned)H) {
+                if ((unsigned)px < (unsigned)W) { float4* d = accq + (long long)py * W + px; red_add_v4((float*)d, pw[0], pw[1], pw[2], pw[3]); }
+                if ((unsigned)pex < (unsigned)W) { float4* d = accq + (long long)py * W + pex; red_add_v4((float*)d, pe[0], pe[1], pe[2], pe[3]); }
+            }
+        }
+
+        // horizontal: this column's E slots are the next lane's W slots when its NW target is (x0 + 1, y0)
+        int ex = ok ? x0 + 1 : kSentinel;
+        {
+            const int rx = __shfl_up_sync(0xffffffffu, ex, 1);
+            const int ry = __shfl_up_sync(0xffffffffu, y0, 1);
+            float rt[4], rb[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int c = q + j;
-                float val = 0.f;
-                if (c < g.C) {
-                    float xv = __ldg(ip + c * in.sc);
-                    if (pre) xv = (xv + 1.f) * 0.5f;   // softSplat.py:334
-                    val = xv * m;                      // softSplat.py:328 / 338
-                } else if (c == g.C && g.CA > g.C) {
-                    val = m;                           // normaliser channel
-                }
-                a[j] = val;
+                rt[j] = __shfl_up_sync(0xffffffffu, tE[j], 1);
+                rb[j] = __shfl_up_sync(0xffffffffu, bE[j], 1);
             }
+            const bool take = (lane > 0) && ok && rx == x0 && ry == y0;
+            if (take) {
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4)
-                if (k.valid[c4])
-                    red_add_v4(dst[c4] + q, a[0] * k.w[c4], a[1] * k.w[c4], a[2] * k.w[c4], a[3] * k.w[c4]);
+                for (int j = 0; j < 4; ++j) { tW[j] += rt[j]; bW[j] += rb[j]; }
+            }
+            const bool taken = __shfl_down_sync(0xffffffffu, (int)take, 1) != 0;
+            if (lane < 31 && taken) {
+                ex = kSentinel;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { tE[j] = 0.f; bE[j] = 0.f; }
+            }
         }
+
+        // the top row is final for this thread: one reduction in the merged case
+        if ((unsigned)y0 < (unsigned)H) {
+            if ((unsigned)x0 < (unsigned)W) { float4* d = accq + (long long)y0 * W + x0; red_add_v4((float*)d, tW[0], tW[1], tW[2], tW[3]); }
+            if ((unsigned)ex < (unsigned)W) { float4* d = accq + (long long)y0 * W + ex; red_add_v4((float*)d, tE[0], tE[1], tE[2], tE[3]); }
+        }
+        px = x0; pex = ex; py = ok ? y0 + 1 : kSentinel;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { pw[j] = bW[j]; pe[j] = bE[j]; }
+    }
+    if ((unsigned)py < (unsigned)H) {
+        if ((unsigned)px < (unsigned)W) { float4* d = accq + (long long)py * W + px; red_add_v4((float*)d, pw[0], pw[1], pw[2], pw[3]); }
+        if ((unsigned)pex < (unsigned)W) { float4* d = accq + (long long)py * W + pex; red_add_v4((float*)d, pe[0], pe[1], pe[2], pe[3]); }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pass 2: normalise + post-scale + interleaved -> NCHW.  One thread per target pixel.
+// Pass 2: normalise + post-scale + quad-interleaved -> NCHW.  One thread per (PX consecutive pixels, channel quad):
+// PX float4 loads of the accumulator (+ PX of the quad holding the normaliser), 4 channel-plane stores of PX floats.
 //   softSplat.py:343-349: norm==0 -> 1, divide, (y - 0.5) * 2 (post-scale in every mode but RAW).
 // ------------------------------------------------------------------------------------------------
+template <int PX>
 __global__ void __launch_bounds__(256) splat_normalise_kernel(const float* __restrict__ acc, float* __restrict__ out,
-                                                              float* __restrict__ norm_out, SplatGeom g) {
+                                                              float* __restrict__ norm_out, SplatGeom g, int Q) {
     const long long HW = (long long)g.H * g.W;
-    const long long total = HW * g.N;
+    const long long pix = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * PX;
+    if (pix >= HW) return;      // PX > 1 only when HW % PX == 0
+    const int q = blockIdx.y % Q, n = blockIdx.y / Q;
     const bool has_norm = g.CA > g.C;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const long long pix = idx % HW;
-        const int n = (int)(idx / HW);
-        const float4* a4 = reinterpret_cast<const float4*>(acc + idx * g.CP);
-        float d = 1.f;
-        if (has_norm) {
-            const float nrm = acc[idx * g.CP + g.C];
-            if (norm_out) norm_out[idx] = nrm;
-            d = (nrm == 0.f) ? 1.f : nrm;
-        }
-        float* op = out + (long long)n * g.C * HW + pix;
-        for (int q = 0; q < g.CP; q += 4) {
-            const float4 s4 = a4[q >> 2];
-            const float s[4] = {s4.x, s4.y, s4.z, s4.w};
+    const float4* accn = reinterpret_cast<const float4*>(acc) + (long long)n * Q * HW;
+    float4 s4[PX];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = q + j;
-                if (c < g.C) {
-                    float yv;
-                    if (g.mode == FLDR_SPLAT_RAW) yv = s[j];
-                    else if (!has_norm) yv = (s[j] - 0.5f) * 2.f;
-                    else yv = (s[j] / d - 0.5f) * 2.f;
-                    op[(long long)c * HW] = yv;
-                }
+    for (int k = 0; k < PX; ++k) s4[k] = __ldcs(accn + q * HW + pix + k);
+    float d[PX];
+#pragma unroll
+    for (int k = 0; k < PX; ++k) d[k] = 1.f;
+    if (has_norm) {
+        const int qn = g.C >> 2, slot = g.C & 3;
+        float nrm[PX];
+#pragma unroll
+        for (int k = 0; k < PX; ++k) {
+            const float4 n4 = (qn == q) ? s4[k] : __ldcs(accn + qn * HW + pix + k);
+            nrm[k] = slot == 0 ? n4.x : slot == 1 ? n4.y : slot == 2 ? n4.z : n4.w;
+            d[k] = (nrm[k] == 0.f) ? 1.f : nrm[k];
+        }
+        if (norm_out && q == 0) vstore<PX>(norm_out + (long long)n * HW + pix, nrm);
+    }
+    float* op = out + (long long)n * g.C * HW + pix;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = q * 4 + j;
+        if (c < g.C) {
+            float yv[PX];
+#pragma unroll
+            for (int k = 0; k < PX; ++k) {
+                const float sv = j == 0 ? s4[k].x : j == 1 ? s4[k].y : j == 2 ? s4[k].z : s4[k].w;
+                if (g.mode == FLDR_SPLAT_RAW) yv[k] = sv;
+                else if (!has_norm) yv[k] = (sv - 0.5f) * 2.f;
+                else yv[k] = (sv / d[k] - 0.5f) * 2.f;
             }
+            vstore<PX>(op + (long long)c * HW, yv);
         }
     }
 }
@@ -306,11 +411,40 @@ extern "C" int fldr_splat_fwd(int mode, const float* in, const int64_t* in_strid
     float* acc = static_cast<float*>(ws);
     cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)N * H * W * g.CP * sizeof(float), s);
     if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
-    const long long total = (long long)N * H * W;
-    splat_scatter_kernel<<<grid_for(total, 256), 256, 0, s>>>(make_view(in, in_strides), make_view(flow, flow_strides),
-                                                              make_view(metric, metric_strides), acc, g);
+    const int Q = g.CP / 4;
+    if ((long long)N * Q > 65535) return FLDR_ERR_UNSUPPORTED;
+    const View4 vin = make_view(in, in_strides), vfl = make_view(flow, flow_strides), vme = make_view(metric, metric_strides);
+    {
+        // small frames: short row runs and narrow blocks keep enough CTAs in flight; large frames: 16-row runs
+        const bool small = (long long)H * W * Q * N < 512 * 1024;
+        const int bx = W >= 128 ? 128 : ((W + 31) / 32) * 32;
+        dim3 grid((W + bx - 1) / bx, small ? (H + 3) / 4 : (H + 15) / 16, N * Q);
+        const int wkind = !g.has_metric ? 0 : (mode == FLDR_SPLAT_SOFTMAX ? 1 : 2);
+        const bool pre = mode == FLDR_SPLAT_SOFTMAX;
+#define FLDR_LAUNCH_SCATTER(WK_, PRE_)                                                                      \
+    do {                                                                                                    \
+        if (small) splat_scatter_merged_kernel<4, WK_, PRE_><<<grid, bx, 0, s>>>(vin, vfl, vme, acc, g, Q);  \
+        else splat_scatter_merged_kernel<16, WK_, PRE_><<<grid, bx, 0, s>>>(vin, vfl, vme, acc, g, Q);       \
+    } while (0)
+        if (wkind == 1) FLDR_LAUNCH_SCATTER(1, true);
+        else if (wkind == 2) FLDR_LAUNCH_SCATTER(2, false);
+        else if (pre) FLDR_LAUNCH_SCATTER(0, true);
+        else FLDR_LAUNCH_SCATTER(0, false);
+#undef FLDR_LAUNCH_SCATTER
+    }
     if ((st = check_launch()) != FLDR_OK) return st;
-    splat_normalise_kernel<<<grid_for(total, 256), 256, 0, s>>>(acc, out, norm, g);
+    {
+        const long long HW = (long long)H * W;
+        const bool px4 = (HW % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                         (!norm || (reinterpret_cast<uintptr_t>(norm) & 15) == 0);
+        if (px4) {
+            dim3 grid((unsigned)((HW / 4 + 255) / 256), N * Q, 1);
+            splat_normalise_kernel<4><<<grid, 256, 0, s>>>(acc, out, norm, g, Q);
+        } else {
+            dim3 grid((unsigned)((HW + 255) / 256), N * Q, 1);
+            splat_normalise_kernel<1><<<grid, 256, 0, s>>>(acc, out, norm, g, Q);
+        }
+    }
     return check_launch();
 }
 
