@@ -17,6 +17,8 @@ SYMBOLS = {
     "fldr_abi_version": (ctypes.c_int, []),
     "fldr_status_string": (ctypes.c_char_p, [ctypes.c_int]),
     "fldr_last_cuda_error": (ctypes.c_int, []),
+    "fldr_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
+    "fldr_get_option": (ctypes.c_int, [ctypes.c_char_p]),
     "fldr_splat_fwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 5),
     "fldr_splat_fwd": (ctypes.c_int, [ctypes.c_int, c_float_p, c_i64_p, c_float_p, c_i64_p, c_float_p, c_i64_p,
                                       c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

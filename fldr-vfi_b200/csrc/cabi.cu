@@ -1,4 +1,7 @@
 // Library-level entry points of include/fldr_b200.h (status strings, error state, device queries).
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace fldr {
@@ -20,6 +23,40 @@ int sm_count() {
 }
 
 }  // namespace fldr
+
+namespace fldr {
+static const char* const kOptionNames[kOptCount] = {"splat_stream", "splat_ring_mb", "splat_lag"};
+static const char* const kOptionEnv[kOptCount] = {"FLDR_SPLAT_STREAM", "FLDR_SPLAT_RING_MB", "FLDR_SPLAT_LAG"};
+static int g_options[kOptCount];
+static bool g_options_init = false;
+static void init_options() {
+    if (g_options_init) return;
+    for (int i = 0; i < kOptCount; ++i) {
+        const char* e = getenv(kOptionEnv[i]);
+        g_options[i] = e ? atoi(e) : 0;
+    }
+    g_options_init = true;
+}
+int get_option(int opt) {
+    init_options();
+    return (opt >= 0 && opt < kOptCount) ? g_options[opt] : 0;
+}
+}  // namespace fldr
+
+extern "C" int fldr_set_option(const char* name, int value) {
+    if (!name) return FLDR_ERR_INVALID_ARGUMENT;
+    fldr::init_options();
+    for (int i = 0; i < fldr::kOptCount; ++i)
+        if (strcmp(name, fldr::kOptionNames[i]) == 0) { fldr::g_options[i] = value; return FLDR_OK; }
+    return FLDR_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int fldr_get_option(const char* name) {
+    if (!name) return 0;
+    for (int i = 0; i < fldr::kOptCount; ++i)
+        if (strcmp(name, fldr::kOptionNames[i]) == 0) return fldr::get_option(i);
+    return 0;
+}
 
 extern "C" int fldr_abi_version(void) { return FLDR_B200_ABI_VERSION; }
 

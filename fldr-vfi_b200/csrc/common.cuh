@@ -33,6 +33,10 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int sm_count();
 
+// tuning / diagnostic options (fldr_set_option); defaults may come from FLDR_<NAME> environment variables
+enum Option { kOptSplatStream = 0, kOptSplatRingMb = 1, kOptSplatLag = 2, kOptCount = 3 };
+int get_option(int opt);
+
 // red.global.add.v4.f32 (sm_90+): one 16-byte reduction request instead of four scalar REDs.
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");

@@ -60,6 +60,16 @@ int fldr_abi_version(void);
 const char* fldr_status_string(int status);
 /* cudaError_t of the most recent failing CUDA call made by this library on the calling thread (0 if none). */
 int fldr_last_cuda_error(void);
+/*
+ * Tuning / diagnostic switches (process-wide; initial values come from FLDR_<NAME> environment variables):
+ *   "splat_stream"   0 (default) whole-frame three-pass splat; 1 = single-launch streaming kernel with an L2-resident
+ *                    ring accumulator (experimental)
+ *   "splat_ring_mb"  ring size cap of the streaming kernel in MiB (0 = 32)
+ *   "splat_lag"      schedule lag of the streaming kernel in strips (0 = automatic)
+ * Results are identical (within the summation-order tolerance) for every setting.
+ */
+int fldr_set_option(const char* name, int value);
+int fldr_get_option(const char* name);
 
 /* ---------------------------------------------------------------- splat ---------------------------------- */
 

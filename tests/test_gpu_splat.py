@@ -210,3 +210,72 @@ def test_feature_splat_L0_vs_oracle_full(cuda_lib):
     yo, gio, _, _ = so.function_softsplat_grads(x, fl, None, "softmax", gout)
     assert_splat_close(y, yo, "feature L0 out")
     assert_splat_close(gi, gio, "feature L0 grad_input")
+
+
+@pytest.fixture
+def streaming(cuda_lib):
+    """Opt into the single-launch streaming kernel for one test."""
+    cuda_lib.fldr_set_option(b"splat_stream", 1)
+    yield
+    cuda_lib.fldr_set_option(b"splat_stream", 0)
+
+
+@pytest.mark.parametrize("shape,regime,with_metric", [
+    ((1, 3, 256, 448), "F1", True), ((1, 48, 32, 56), "F2", False), ((2, 5, 33, 47), "FB", True), ((3, 7, 5, 130), "F2", False),
+])
+def test_streaming_kernel_small_frames(cuda_lib, streaming, shape, regime, with_metric):
+    S = _mods(cuda_lib)
+    N, C, H, W = shape
+    x = synth.features(N, C, H, W, seed=11)
+    fl = synth.flow(N, H, W, regime, seed=12)
+    z = synth.metric(N, H, W, seed=13) if with_metric else None
+    y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), None if z is None else z.cuda(), "softmax")
+    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "streaming small", mag=1.0)
+
+
+def test_streaming_kernel_4k(cuda_lib, streaming):
+    S = _mods(cuda_lib)
+    x = synth.image(1, 3, H4K, W4K, seed=56)
+    fl = synth.flow(1, H4K, W4K, "F1", seed=57)
+    z = synth.metric(1, H4K, W4K, seed=58)
+    y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), z.cuda(), "softmax")
+    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "4K streaming", mag=1.0)
+
+
+def test_bounded_ring_overflow_falls_back(cuda_lib, streaming):
+    """Frames taller than the L2-resident ring bound the vertical reach of the streaming kernel; a flow beyond it must
+    flag the overflow on the device and re-do the call with the whole-frame path (no host sync) - same result."""
+    S = _mods(cuda_lib)
+    H, W = 1152, 4096                      # ring for W=4096 holds 512 rows -> reach ~88 rows
+    x = synth.image(1, 3, H, W, seed=81)
+    z = synth.metric(1, H, W, seed=82)
+    fl = synth.flow(1, H, W, "F1", seed=83)
+    fl[:, 1, 300:340, 1000:1400] += 260.0      # a block moving 260 rows down: beyond the reach
+    fl[:, 1, 900:930, 2000:2100] -= 400.0      # and one moving 400 rows up
+    y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), z.cuda(), "softmax")
+    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "overflow fallback", mag=1.0)
+    # and the in-reach case on the same shape (pure streaming path) for contrast
+    fl2 = synth.flow(1, H, W, "F1", seed=84)
+    fl2[:, 1, 300:340, 1000:1400] += 150.0
+    y2 = S.FunctionSoftsplat(x.cuda(), fl2.cuda(), z.cuda(), "softmax")
+    assert_splat_close(y2, so.function_softsplat(x, fl2, z, "softmax"), "in-reach streaming", mag=1.0)
+
+
+def test_batched_tall_frames_stream(cuda_lib, streaming):
+    """N > 1 with a ring smaller than the batch: strips of consecutive samples share ring slots across epochs."""
+    S = _mods(cuda_lib)
+    N, H, W = 3, 640, 4096
+    x = synth.image(N, 3, H, W, seed=91)
+    z = synth.metric(N, H, W, seed=92)
+    fl = synth.flow(N, H, W, "F1", seed=93)
+    g = synth.grad((N, 3, H, W), seed=94)
+    xd, fd, zd = x.cuda().requires_grad_(True), fl.cuda().requires_grad_(True), z.cuda().requires_grad_(True)
+    y = S.FunctionSoftsplat(xd, fd, zd, "softmax")
+    yo, gi, gf, gz = so.function_softsplat_grads(x, fl, z, "softmax", g)
+    # fp64 oracle on the same fp32 coordinates' inputs: its distance from the fp32 oracle measures conditioning
+    _, gi64, gf64, gz64 = so.function_softsplat_grads(x.double(), fl.double(), z.double(), "softmax", g.double())
+    assert_splat_close(y, yo, "batched tall out", mag=1.0)
+    grads = torch.autograd.grad(y, [xd, fd, zd], g.cuda())
+    assert_splat_close(grads[0], gi, "batched tall grad_input", cond=gi - gi64)
+    assert_splat_close(grads[1], gf, "batched tall grad_flow", cond=gf - gf64)
+    assert_splat_close(grads[2], gz, "batched tall grad_metric", cond=gz - gz64)

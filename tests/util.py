@@ -18,7 +18,7 @@ def load_golden(name):
     return {k: torch.from_numpy(z[k]) for k in z.files}
 
 
-def assert_splat_close(got, ref, what="", mag=None):
+def assert_splat_close(got, ref, what="", mag=None, cond=None):
     """|got-ref| <= atol*mag + rtol*|ref|.  ``mag`` (default max(1, max|ref|)) scales the absolute part for
     un-normalised quantities (raw sums, gradients) whose magnitude is not O(1); for the normalised splat
     output (|y| <= 1) it is 1 and the bound is exactly the north_star's 1e-4 abs / 1e-5 rel."""
@@ -29,6 +29,10 @@ def assert_splat_close(got, ref, what="", mag=None):
         mag = max(1.0, float(ref.abs().max()))
     err = (got - ref).abs()
     bound = SPLAT_ATOL * mag + SPLAT_RTOL * ref.abs()
+    if cond is not None:
+        # ill-conditioned elements (gradients through a near-zero normaliser cancel terms ~1/norm): allow 10x the
+        # oracle's own fp32-vs-fp64 discrepancy at that element on top of the flat bound
+        bound = bound + 10.0 * cond.detach().double().cpu().abs()
     bad = err > bound
     assert not bool(bad.any()), f"{what}: {int(bad.sum())} elements out of tolerance, max err {float(err.max()):.3e} (mag {mag:.3g})"
 
