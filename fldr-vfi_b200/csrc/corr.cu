@@ -104,9 +104,10 @@ __global__ void __launch_bounds__(fwd::NT) corr81_fwd_kernel(View4 f1, View4 f2,
 // full/empty mbarrier ring keeps the loads STAGES-1 chunks ahead of the FFMA loop, across tile boundaries.
 // ------------------------------------------------------------------------------------------------
 namespace fwdtma {
-constexpr int TW = 32, CK = 8, STAGES = 3;
+constexpr int TW = 32, CK = 8;
 template <int TH> struct Cfg {
     static constexpr int NT = 8 * TH * 3;
+    static constexpr int STAGES = TH == 16 ? 4 : 3;        // 4 x 46 KB (1 CTA/SM) or 3 x 28 KB (2 CTAs/SM)
     static constexpr int F2H = TH + 2 * kPad, F2W = TW + 2 * kPad;
     static constexpr int S1 = CK * TH * TW, S2 = CK * F2H * F2W;       // floats
     static constexpr int STAGE_BYTES = (S1 + S2) * 4;
@@ -114,12 +115,17 @@ template <int TH> struct Cfg {
 };
 }  // namespace fwdtma
 
-template <int TH>
+// SPLIT: the channel range of a tile is divided over `ksplit` work items (small pyramid levels have fewer tiles than
+// the GPU has SMs: 20 tiles x 25 chunks at C = 196); partial sums are reduced into the zero-filled output with
+// red.global.add.v4.f32.
+template <int TH, bool SPLIT>
 __global__ void __launch_bounds__(fwdtma::Cfg<TH>::NT, TH == 8 ? 2 : 1)
 corr81_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
-                      float* __restrict__ out, int B, int C, int H, int W, int tilesX, int tilesY) {
+                      float* __restrict__ out, int B, int C, int H, int W, int tilesX, int tilesY, int ksplit,
+                      int chunks_per_split) {
     using namespace fwdtma;
     using K = Cfg<TH>;
+    constexpr int STAGES = K::STAGES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * K::STAGE_BYTES);
     uint64_t* empty = full + STAGES;
@@ -135,32 +141,57 @@ corr81_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_cons
     }
     __syncthreads();
 
-    const int nchunks = (C + CK - 1) / CK;
-    const int ntiles = tilesX * tilesY * B;
-    const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const long long total = (long long)my_tiles * nchunks;
+    const int nchunks_all = (C + CK - 1) / CK;
+    const int nitems = tilesX * tilesY * B * ksplit;
+    const int my_items = ((int)blockIdx.x < nitems) ? (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    // chunks of item `it`: [c_begin, c_end) ; every item of this CTA has the same split geometry except the last split
+    auto item_chunks = [&](int it, int& tile, int& c_begin, int& c_end) {
+        const int ks = SPLIT ? it % ksplit : 0;
+        tile = SPLIT ? it / ksplit : it;
+        c_begin = ks * chunks_per_split;
+        c_end = min(nchunks_all, c_begin + chunks_per_split);
+    };
 
-    auto issue = [&](long long g) {     // thread 0 only
-        const int tl = (int)(g / nchunks), ch = (int)(g % nchunks);
-        const int tile = blockIdx.x + tl * gridDim.x;
+    // producer cursor (thread 0 only) lives in shared memory: it must not cost the 383 consumer threads registers
+    __shared__ int ps[6];        // [0] item (local index), [1] tile, [2] chunk end, [3] next chunk, [4] chunks issued
+    if (tid == 0) {
+        int tile = 0, cb = 0, ce = 0;
+        if (my_items > 0) item_chunks(blockIdx.x, tile, cb, ce);
+        ps[0] = 0; ps[1] = tile; ps[2] = ce; ps[3] = cb; ps[4] = 0;
+    }
+    auto issue_next = [&]() {     // thread 0 only
+        const int il = ps[0];
+        if (il >= my_items) return;
+        const int tile = ps[1], ch = ps[3], prod = ps[4];
         const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, b = tile / (tilesX * tilesY);
-        const int st = (int)(g % STAGES);
-        if (g >= STAGES) mbar_wait(&empty[st], (uint32_t)((g / STAGES - 1) & 1));
+        const int st = prod % STAGES;
+        if (prod >= STAGES) mbar_wait(&empty[st], (uint32_t)((prod / STAGES - 1) & 1));
         float* s1 = reinterpret_cast<float*>(smem_raw + st * K::STAGE_BYTES);
         float* s2 = s1 + K::S1;
         mbar_arrive_expect_tx(&full[st], K::STAGE_BYTES);
         tma_load_4d(s1, &tm1, &full[st], tx * TW, ty * TH, ch * CK, b);
         tma_load_4d(s2, &tm2, &full[st], tx * TW - kPad, ty * TH - kPad, ch * CK, b);
+        ps[4] = prod + 1;
+        if (ch + 1 >= ps[2]) {
+            ps[0] = il + 1;
+            if (il + 1 < my_items) {
+                int ntile, cb, ce;
+                item_chunks(blockIdx.x + (il + 1) * gridDim.x, ntile, cb, ce);
+                ps[1] = ntile; ps[2] = ce; ps[3] = cb;
+            }
+        } else {
+            ps[3] = ch + 1;
+        }
     };
-
-    long long prod = 0;
     if (tid == 0)
-        for (; prod < total && prod < STAGES - 1; ++prod) issue(prod);
+        for (int i = 0; i < STAGES - 1; ++i) issue_next();
 
     const float rc = 1.0f / (float)C;
     const long long HW = (long long)H * W;
-    long long g = 0;
-    for (int tl = 0; tl < my_tiles; ++tl) {
+    int g = 0;
+    for (int il = 0; il < my_items; ++il) {
+        int tile, c_begin, c_end;
+        item_chunks(blockIdx.x + il * gridDim.x, tile, c_begin, c_end);
         float acc[3][kD][4];
 #pragma unroll
         for (int d = 0; d < 3; ++d)
@@ -169,8 +200,8 @@ corr81_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[d][o][j] = 0.f;
 
-        for (int ch = 0; ch < nchunks; ++ch, ++g) {
-            if (tid == 0 && prod < total) { issue(prod); ++prod; }
+        for (int ch = c_begin; ch < c_end; ++ch, ++g) {
+            if (tid == 0) issue_next();
             const int st = (int)(g % STAGES);
             mbar_wait(&full[st], (uint32_t)((g / STAGES) & 1));
             const float* s1 = reinterpret_cast<const float*>(smem_raw + st * K::STAGE_BYTES);
@@ -196,7 +227,6 @@ corr81_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_cons
             if ((tid & 31) == 0) mbar_arrive(&empty[st]);
         }
 
-        const int tile = blockIdx.x + tl * gridDim.x;
         const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, b = tile / (tilesX * tilesY);
         const int y = ty * TH + row, x = tx * TW + pg * 4;
         if (y < H && x < W) {      // W % 4 == 0 on this path: the 4-pixel group is all in or all out
@@ -204,9 +234,12 @@ corr81_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_cons
 #pragma unroll
             for (int d = 0; d < 3; ++d)
 #pragma unroll
-                for (int o = 0; o < kD; ++o)
-                    __stcs(reinterpret_cast<float4*>(ob + (long long)((dyg * 3 + d) * kD + o) * HW),
-                           make_float4(acc[d][o][0] * rc, acc[d][o][1] * rc, acc[d][o][2] * rc, acc[d][o][3] * rc));
+                for (int o = 0; o < kD; ++o) {
+                    float* op = ob + (long long)((dyg * 3 + d) * kD + o) * HW;
+                    if (SPLIT) red_add_v4(op, acc[d][o][0] * rc, acc[d][o][1] * rc, acc[d][o][2] * rc, acc[d][o][3] * rc);
+                    else __stcs(reinterpret_cast<float4*>(op),
+                                make_float4(acc[d][o][0] * rc, acc[d][o][1] * rc, acc[d][o][2] * rc, acc[d][o][3] * rc));
+                }
         }
     }
 }
@@ -225,15 +258,33 @@ static int launch_fwd_tma(const View4& f1, const View4& f2, float* out, int B, i
     const uint32_t box2[4] = {(uint32_t)K::F2W, (uint32_t)K::F2H, CK, 1};
     if (!encode_tensor_map_4d(&tm1, f1.p, dims, st1, box1) || !encode_tensor_map_4d(&tm2, f2.p, dims, st2, box2))
         return FLDR_OK;   // not describable: caller falls back to the generic kernel
-    {   // per device, cheap: raise the dynamic shared memory limit every launch (one process may drive several GPUs)
-        cudaError_t e = cudaFuncSetAttribute(corr81_fwd_tma_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
-        if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
-    }
     const int tilesX = (W + TW - 1) / TW, tilesY = (H + TH - 1) / TH;
     const int ntiles = tilesX * tilesY * B;
     const int per_sm = (TH == 8) ? 2 : 1;
-    const int grid = ntiles < sm_count() * per_sm ? ntiles : sm_count() * per_sm;
-    corr81_fwd_tma_kernel<TH><<<grid, K::NT, K::SMEM_BYTES, s>>>(tm1, tm2, out, B, C, H, W, tilesX, tilesY);
+    const int slots = sm_count() * per_sm;
+    const int nchunks = (C + CK - 1) / CK;
+    // fewer tiles than CTA slots: split the channel range so every SM has work
+    int ksplit = 1;
+    if (ntiles * 2 <= slots && nchunks >= 2) {
+        ksplit = slots / ntiles;
+        if (ksplit > nchunks) ksplit = nchunks;
+    }
+    const int cps = (nchunks + ksplit - 1) / ksplit;
+    ksplit = (nchunks + cps - 1) / cps;
+    const int nitems = ntiles * ksplit;
+    const int grid = nitems < slots ? nitems : slots;
+    cudaError_t e;
+    if (ksplit > 1) {
+        e = cudaMemsetAsync(out, 0, (size_t)B * 81 * H * W * sizeof(float), s);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
+        e = cudaFuncSetAttribute(corr81_fwd_tma_kernel<TH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
+        corr81_fwd_tma_kernel<TH, true><<<grid, K::NT, K::SMEM_BYTES, s>>>(tm1, tm2, out, B, C, H, W, tilesX, tilesY, ksplit, cps);
+    } else {
+        e = cudaFuncSetAttribute(corr81_fwd_tma_kernel<TH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
+        corr81_fwd_tma_kernel<TH, false><<<grid, K::NT, K::SMEM_BYTES, s>>>(tm1, tm2, out, B, C, H, W, tilesX, tilesY, 1, nchunks);
+    }
     *used = true;
     return check_launch();
 }
