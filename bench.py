@@ -261,9 +261,59 @@ def run_ours(args, rank, world, local_rank):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(frac=1.0 / 8)
+        if world == 1 and not args.no_ref_gpu:
+            line["ref_gpu"] = ref_gpu_baseline(devin, args)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------- reference on the GPU
+def ref_gpu_baseline(devin, args):
+    """The reference's own CuPy kernels on the same B200 (north_star's first reported baseline): the UNMODIFIED
+    softSplat.py / OpticalFlow/correlation.py staged in baseline/_ref, CuPy replaced by an NVRTC shim
+    (baseline/cupy_shim).  Same inputs, same step, device-resident, CUDA events.  A reported baseline, not a target."""
+    try:
+        from baseline import ref_gpu
+        if not ref_gpu.available():
+            return {"unavailable": "baseline/_ref not staged (python baseline/fetch_ref.py in the build container)"}
+        RS = ref_gpu.softsplat_module()
+        RC = ref_gpu.correlation_module()
+        splat = RS.Softsplat()
+
+        def run_call(name, t):
+            if name.startswith("splat"):
+                return splat(t["x"], t["flow"], t["z"])
+            return RC.FunctionCorrelation(tensorFirst=t["f1"], tensorSecond=t["f2"])
+
+        steps = max(1, min(args.steps, 5))
+        with torch.no_grad():
+            for _ in range(3):                      # NVRTC compiles per shape on first use
+                for n, t in devin:
+                    run_call(n, t)
+            ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in devin] for _ in range(steps)]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for s in range(steps):
+                for i, (n, t) in enumerate(devin):
+                    ev[s][i][0].record()
+                    run_call(n, t)
+                    ev[s][i][1].record()
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        agg = {}
+        for i, (n, _) in enumerate(devin):
+            a = agg.setdefault(n, [0.0, 0])
+            a[0] += sum(ev[s][i][0].elapsed_time(ev[s][i][1]) for s in range(steps)) / steps
+            a[1] += 1
+        return {"value": 1000.0 / ms, "unit": "frame-pairs/s", "ms_per_step": ms, "steps": steps,
+                "what": "unmodified reference op files + their CuPy kernel strings via NVRTC on this GPU, whole "
+                        "FunctionSoftsplat / FunctionCorrelation calls (host templating included)",
+                "ms_per_call": {k: round(v[0] / v[1], 4) for k, v in agg.items()}}
+    except Exception as exc:          # a reported baseline must never take the bench down
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
 
 
 # ----------------------------------------------------------------------------------------------- CPU arms
@@ -345,6 +395,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -348,7 +348,7 @@ __device__ __forceinline__ void st_cg4(float4* p, float4 v) {
 
 // ctrl layout (unsigned): [0] next item, [1] overflow flag, [2 .. 2+NT) sdone[J], [2+NT .. +RS) clean[slot],
 // then nread[J * T + t] (readers of the normaliser quad per strip tile, Q > 1 only)
-template <int WKIND, bool PRE>
+template <int WKIND, bool PRE, int QS>
 __global__ void __launch_bounds__(stream::TWC) splat_stream_kernel(View4 in, View4 flow, View4 metric,
                                                                    float4* __restrict__ ring, unsigned* __restrict__ ctrl,
                                                                    float* __restrict__ out, float* __restrict__ norm_out,
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(stream::TWC) splat_stream_kernel(View4 in, Vie
             if (jhi == sg.NS - 1) ra.yhi = H;   // bottom strip: rows >= H are dropped by the frame test anyway
             if (jlo == 0) ra.ylo = -1;
             const int yb = j * R;
-            const bool ovf = scatter_rows<WKIND, PRE, 0>(in, flow, metric, g, n, q, x, yb, min(R, H - yb), ra);
+            const bool ovf = scatter_rows<WKIND, PRE, QS>(in, flow, metric, g, n, q, x, yb, min(R, H - yb), ra);
             if (ovf) s_overflow = 1;
             __threadfence();
             __syncthreads();
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(stream::TWC) splat_stream_kernel(View4 in, Vie
                             for (int k = 0; k < 4; ++k) {
                                 n4[k] = (qn == q) ? s4[k] : ld_cg4(rn + ro + k);
                                 nrm[k] = slot == 0 ? n4[k].x : slot == 1 ? n4[k].y : slot == 2 ? n4[k].z : n4[k].w;
-                                d[k] = (nrm[k] == 0.f) ? 1.f : nrm[k];
+                                d[k] = (nrm[k] == 0.f) ? 1.f : __frcp_rn(nrm[k]);
                             }
                             if (norm_out && q == 0) vstore<4>(norm_out + (long long)n * HW + (long long)y * W + xg, nrm);
                         }
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(stream::TWC) splat_stream_kernel(View4 in, Vie
                                     const float sv = c4 == 0 ? s4[k].x : c4 == 1 ? s4[k].y : c4 == 2 ? s4[k].z : s4[k].w;
                                     if (g.mode == FLDR_SPLAT_RAW) yv[k] = sv;
                                     else if (!has_norm) yv[k] = (sv - 0.5f) * 2.f;
-                                    else yv[k] = (sv / d[k] - 0.5f) * 2.f;
+                                    else yv[k] = (sv * d[k] - 0.5f) * 2.f;
                                 }
                                 vstore<4>(op + (long long)c * HW + (long long)y * W + xg, yv);
                             }
@@ -856,19 +856,27 @@ extern "C" int fldr_splat_fwd(int mode, const float* in, const int64_t* in_strid
         static int ctas_per_sm = 0;
         if (ctas_per_sm == 0) {
             int nb = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, splat_stream_kernel<1, true>, stream::TWC, 0) != cudaSuccess || nb < 1) nb = 4;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, splat_stream_kernel<1, true, 0>, stream::TWC, 0) != cudaSuccess || nb < 1) nb = 4;
             ctas_per_sm = nb > stream::kCtasPerSm ? stream::kCtasPerSm : nb;
         }
         long long grid = (long long)sm_count() * ctas_per_sm;
         if (grid > p.sg.total) grid = p.sg.total;
         const int wkind = !g.has_metric ? 0 : (g.mode == FLDR_SPLAT_SOFTMAX ? 1 : 2);
         const bool pre = g.mode == FLDR_SPLAT_SOFTMAX;
-#define FLDR_LAUNCH_STREAM(WK_, PRE_) \
-    splat_stream_kernel<WK_, PRE_><<<(unsigned)grid, stream::TWC, 0, s>>>(vin, vfl, vme, ring, ctrl, out, norm, g, p.sg)
+        const int qs = (g.C == 3 && g.CA == 4) ? 1 : (g.CA == g.C && g.C % 4 == 0) ? 2 : 0;
+#define FLDR_LAUNCH_STREAM2(WK_, PRE_, QS_) \
+    splat_stream_kernel<WK_, PRE_, QS_><<<(unsigned)grid, stream::TWC, 0, s>>>(vin, vfl, vme, ring, ctrl, out, norm, g, p.sg)
+#define FLDR_LAUNCH_STREAM(WK_, PRE_)                        \
+    do {                                                     \
+        if (qs == 1) FLDR_LAUNCH_STREAM2(WK_, PRE_, 1);      \
+        else if (qs == 2) FLDR_LAUNCH_STREAM2(WK_, PRE_, 2); \
+        else FLDR_LAUNCH_STREAM2(WK_, PRE_, 0);              \
+    } while (0)
         if (wkind == 1) FLDR_LAUNCH_STREAM(1, true);
         else if (wkind == 2) FLDR_LAUNCH_STREAM(2, false);
         else if (pre) FLDR_LAUNCH_STREAM(0, true);
         else FLDR_LAUNCH_STREAM(0, false);
+#undef FLDR_LAUNCH_STREAM2
 #undef FLDR_LAUNCH_STREAM
         if ((st = check_launch()) != FLDR_OK) return st;
     }
