@@ -90,3 +90,24 @@ class _Cuda:
 
 
 cuda = _Cuda()
+
+
+# ---- non-hot-path helpers the reference model files reference at module / setup time (fLDRnet.py:232-264,
+# pca_comp.py:353,372; useful.py:68-73).  numpy-backed; never used inside the timed forward.
+def asnumpy(a):
+    import numpy as np
+    return np.asarray(a)
+
+
+def asarray(a):
+    import numpy as np
+    return np.asarray(a)
+
+
+class _Pool:
+    def free_all_blocks(self):
+        pass
+
+
+def get_default_memory_pool():
+    return _Pool()

@@ -1,0 +1,144 @@
+"""End-to-end harness: the UNTOUCHED fLDRnet (`--papermodel --test5scales`, shipped checkpoint) on one seeded synthetic
+4096x2160 triplet, once with the reference's own CuPy kernels (NVRTC shim) and once with the sm_100a drop-ins.
+
+    python baseline/e2e_fldrnet.py            # runs both variants in subprocesses, prints one JSON line
+    python baseline/e2e_fldrnet.py --impl ours|reference --out /tmp/x.pt     (worker)
+
+BASELINE.json config[2] / north_star (c): PSNR of the interpolated frame against the synthetic ground truth must
+agree within 0.01 dB between the two variants; e2e frame-pairs/s = 1 / median model_net(...) time.
+
+The model files, their runner and the checkpoint are the reference's, staged unmodified in baseline/_ref/ by
+baseline/fetch_ref.py.  Harness-side accommodations (none touches a reference file): sys.path ordering (drop-ins
+first for `ours`), stub `skimage`, shim `cupy`, `torch.load(weights_only=False)` (torch >= 2.6 default breaks
+utils.py:93), cwd = baseline/_ref so `./checkpoint_dir/...` resolves.  The padding / pyramid / model call restate
+run_on_your_images.py:118-153 because that function also writes PNGs and evaluates on the host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REFDIR = os.path.join(HERE, "_ref")
+
+
+def synthetic_triplet(H=2160, W=4096, seed=0):
+    """frame0 = band-limited noise; frame1 / frame_t = frame0 backward-warped by a smooth flow at t=1 / t=0.5."""
+    import torch
+    import torch.nn.functional as F
+    sys.path.insert(0, ROOT)
+    from oracle import synth
+    img0 = synth.image(1, 3, H, W, seed=seed)
+    flow = synth.flow(1, H, W, "F1", seed=seed + 1)
+    gy, gx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+
+    def warp(t):
+        x = (gx + t * flow[0, 0]) / (W - 1) * 2 - 1
+        y = (gy + t * flow[0, 1]) / (H - 1) * 2 - 1
+        return F.grid_sample(img0, torch.stack([x, y], -1).unsqueeze(0), mode="bilinear", padding_mode="border", align_corners=True)
+
+    img1, imgt = warp(1.0), warp(0.5)
+    return torch.stack([img0[0], img1[0], imgt[0]], 0).permute(1, 0, 2, 3).unsqueeze(0).contiguous()   # [1,3,T=3,H,W]
+
+
+def worker(impl, out_path, reps, height, width):
+    import torch
+    if impl == "ours":
+        sys.path.insert(0, os.path.join(ROOT, "fldr-vfi_b200", "dropin"))
+    sys.path.insert(1, REFDIR)
+    sys.path.append(os.path.join(HERE, "cupy_shim"))
+    sys.path.append(os.path.join(HERE, "stubs"))
+    os.chdir(REFDIR)
+    _load = torch.load
+    torch.load = lambda *a, **k: _load(*a, **{**k, "weights_only": k.get("weights_only", False)})
+    import warnings
+    warnings.simplefilter("ignore")
+    sys.argv = ["run_on_your_images.py"]
+    import run_on_your_images as R          # the reference's runner: parse_args / args_config / prepare_model
+    import softSplat
+    import torch.nn.functional as F
+    from torch.autograd import Variable
+    which = os.path.abspath(softSplat.__file__)
+    model_net, device, args = R.prepare_model()
+    model_net.eval()
+    frames = synthetic_triplet(height, width)
+    t_value = torch.tensor([[0.5]])
+    times = []
+    with torch.no_grad():
+        frameT = frames[:, :, -1]
+        input_frames = frames[:, :, :-1]
+        B, C, T, H, W = input_frames.size()
+        OH, OW = H, W
+        input_frames = input_frames.reshape(B, -1, H, W)
+        div_pad = (2 ** args.S_tst) * 8                                     # run_on_your_images.py:127
+        Hp, Wp = (div_pad - H % div_pad) % div_pad, (div_pad - W % div_pad) % div_pad
+        input_frames = F.pad(input_frames, (0, Wp, 0, Hp), args.padding).reshape(B, C, T, OH + Hp, OW + Wp)
+        B, C, T, H, W = input_frames.shape
+        input_gpu = [F.interpolate(input_frames.permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W),
+                                   scale_factor=args.scales[0] / args.scales[i], mode="bicubic",
+                                   align_corners=args.align_cornerse).to(device)
+                     .reshape(B, T, C, int(H * (args.scales[0] / args.scales[i])), int(W * (args.scales[0] / args.scales[i])))
+                     .permute(0, 2, 1, 3, 4) if i != 0 else input_frames.to(device) for i in range(args.S_tst + 1)]
+        t_dev = Variable(t_value.to(device))
+        pred = None
+        for rep in range(reps + 1):                                           # first pass = warm-up (NVRTC, cudnn)
+            input_gpuList = [torch.zeros((B, int(args.img_ch * 2 * (8 ** 2) * 0.25), H // 8, W // 8), device=device) for _ in range(6)]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pred, _ = model_net(input_gpuList, t_dev, normInput=[im.clone() for im in input_gpu], is_training=False, validation=False)
+            torch.cuda.synchronize()
+            if rep > 0:
+                times.append(time.perf_counter() - t0)
+        pred = pred.detach().float().cpu()[0][:, :OH, :OW]
+    import numpy as np
+    out_img = np.around((pred.numpy().transpose(1, 2, 0) + 1) * 127.5)              # denorm255 + round (main.py:894-895)
+    tgt_img = (frameT[0].numpy().transpose(1, 2, 0) + 1) * 127.5
+    mse = float(np.mean((out_img.astype(np.float64) - tgt_img.astype(np.float64)) ** 2))
+    psnr = 10.0 * np.log10(255.0 ** 2 / mse) if mse > 0 else float("inf")            # utils.py:644-659
+    torch.save({"pred": pred, "psnr": psnr, "times": times, "softSplat": which}, out_path)
+    print(json.dumps({"impl": impl, "psnr": psnr, "median_s": sorted(times)[len(times) // 2], "softSplat": which}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--impl", default=None, choices=["ours", "reference"])
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--width", type=int, default=4096)
+    a = ap.parse_args()
+    if a.impl:
+        worker(a.impl, a.out, a.reps, a.height, a.width)
+        return
+    import torch
+    res = {}
+    for tag in ("reference", "reference_again", "ours"):
+        impl = "reference" if tag.startswith("reference") else "ours"
+        out = f"/tmp/fldr_e2e_{tag}.pt"
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", impl, "--out", out, "--reps", str(a.reps),
+                            "--height", str(a.height), "--width", str(a.width)], capture_output=True, text=True)
+        if r.returncode != 0:
+            print(json.dumps({"e2e_fldrnet": "failed", "impl": impl, "stderr": r.stderr[-1500:]}))
+            sys.exit(1)
+        res[tag] = torch.load(out, weights_only=False)
+    d = (res["ours"]["pred"] - res["reference"]["pred"]).abs()
+    # the reference's own atomics are unordered too: its run-to-run difference calibrates the figure above
+    dr = (res["reference_again"]["pred"] - res["reference"]["pred"]).abs()
+    res.pop("reference_again")
+    med = {k: sorted(v["times"])[len(v["times"]) // 2] for k, v in res.items()}
+    print(json.dumps({
+        "e2e_fldrnet": "ok", "frame": f"{a.width}x{a.height}", "reps": a.reps,
+        "psnr_reference_kernels_dB": res["reference"]["psnr"], "psnr_ours_dB": res["ours"]["psnr"],
+        "psnr_abs_diff_dB": abs(res["ours"]["psnr"] - res["reference"]["psnr"]),
+        "max_abs_output_diff": float(d.max()), "mean_abs_output_diff": float(d.mean()),
+        "reference_run_to_run_max_abs_diff": float(dr.max()), "reference_run_to_run_mean_abs_diff": float(dr.mean()),
+        "model_forward_s": med, "frame_pairs_per_s": {k: 1.0 / v for k, v in med.items()},
+        "e2e_speedup": med["reference"] / med["ours"],
+        "softSplat_module": {k: v["softSplat"] for k, v in res.items()}}))
+
+
+if __name__ == "__main__":
+    main()

@@ -11,7 +11,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("FLDR_REFERENCE_DIR", "/root/reference")
 DST = os.path.join(HERE, "_ref")
-FILES = ["softSplat.py", os.path.join("OpticalFlow", "correlation.py")]
+FILES = ["softSplat.py", os.path.join("OpticalFlow", "correlation.py"),
+         # end-to-end harness (baseline/e2e_fldrnet.py): the untouched model + its runner + the shipped checkpoint
+         "fLDRnet.py", "useful.py", "pca_comp.py", "utils.py", "inter4kreader.py", "run_on_your_images.py",
+         os.path.join("OpticalFlow", "PWCNet.py"),
+         os.path.join("checkpoint_dir", "fLDRnet_X4K1000FPS_exp1", "fLDRnet_X4K1000FPS_exp1_best_PSNR.pt")]
 
 
 def fetch(verbose=True):

@@ -1,0 +1,26 @@
+"""End-to-end drop-in test: the untouched fLDRnet (reference files staged in baseline/_ref, shipped checkpoint) gives
+the same interpolated frame with the sm_100a drop-ins as with its own CuPy kernels - PSNR within 0.01 dB (north_star c).
+Reduced frame size to keep the GPU suite short; bench-scale 4K numbers live in profiles/ (baseline/e2e_fldrnet.py)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.path.exists(os.path.join(REF, "fLDRnet.py")), reason="baseline/_ref not staged")]
+
+
+def test_fldrnet_psnr_parity_with_dropins():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "e2e_fldrnet.py"), "--reps", "1",
+                        "--height", "720", "--width", "1280"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["e2e_fldrnet"] == "ok"
+    assert d["softSplat_module"]["ours"].endswith(os.path.join("dropin", "softSplat.py"))
+    assert d["softSplat_module"]["reference"].endswith(os.path.join("_ref", "softSplat.py"))
+    assert d["psnr_abs_diff_dB"] <= 0.01, d
