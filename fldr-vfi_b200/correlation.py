@@ -14,28 +14,33 @@ is one batched launch per gradient instead of one per sample (365, 385).
 import torch
 
 from . import _lib
-from .softSplat import _check_cuda_f32, _device_of, _stream_ptr, _workspace
+from .softSplat import _cached_ws_bytes, _check_cuda_f32, _device_of, _stream_ptr, _workspace
+
+
+def _corr_forward(first, second):
+    if not first.is_cuda:
+        raise NotImplementedError()                      # correlation.py:343-344
+    _check_cuda_f32("first", first)
+    _check_cuda_f32("second", second)
+    assert (first.is_contiguous() == True)               # correlation.py:302
+    assert (second.is_contiguous() == True)              # correlation.py:303
+    assert first.shape == second.shape
+    lib = _lib.lib()
+    B, C, H, W = first.shape
+    output = torch.empty((B, 81, H, W), dtype=torch.float32, device=first.device)
+    ws_bytes = _cached_ws_bytes(lib.fldr_corr81_fwd_workspace_bytes, B, C, H, W)
+    ws = _workspace(ws_bytes, first.device)
+    with _device_of(first):
+        st = lib.fldr_corr81_fwd(_lib.ptr(first), _lib.strides(first), _lib.ptr(second), _lib.strides(second),
+                                 _lib.ptr(output), B, C, H, W, _lib.ptr(ws), ws_bytes, _stream_ptr(first.device))
+    _lib.check(st)
+    return output
 
 
 class _FunctionCorrelation(torch.autograd.Function):
     @staticmethod
     def forward(self, first, second):
-        if not first.is_cuda:
-            raise NotImplementedError()                      # correlation.py:343-344
-        _check_cuda_f32("first", first)
-        _check_cuda_f32("second", second)
-        assert (first.is_contiguous() == True)               # correlation.py:302
-        assert (second.is_contiguous() == True)              # correlation.py:303
-        assert first.shape == second.shape
-        lib = _lib.lib()
-        B, C, H, W = first.shape
-        output = torch.empty((B, 81, H, W), dtype=torch.float32, device=first.device)
-        ws_bytes = lib.fldr_corr81_fwd_workspace_bytes(B, C, H, W)
-        ws = _workspace(ws_bytes, first.device)
-        with _device_of(first):
-            st = lib.fldr_corr81_fwd(_lib.ptr(first), _lib.strides(first), _lib.ptr(second), _lib.strides(second),
-                                     _lib.ptr(output), B, C, H, W, _lib.ptr(ws), ws_bytes, _stream_ptr(first.device))
-        _lib.check(st)
+        output = _corr_forward(first, second)
         self.save_for_backward(first, second)
         return output
 
@@ -48,7 +53,7 @@ class _FunctionCorrelation(torch.autograd.Function):
         B, C, H, W = first.shape
         gradFirst = torch.empty_like(first) if self.needs_input_grad[0] else None
         gradSecond = torch.empty_like(first) if self.needs_input_grad[1] else None
-        ws_bytes = lib.fldr_corr81_bwd_workspace_bytes(B, C, H, W)
+        ws_bytes = _cached_ws_bytes(lib.fldr_corr81_bwd_workspace_bytes, B, C, H, W)
         ws = _workspace(ws_bytes, first.device)
         with _device_of(first):
             st = lib.fldr_corr81_bwd(_lib.ptr(first), _lib.strides(first), _lib.ptr(second), _lib.strides(second),
@@ -59,6 +64,8 @@ class _FunctionCorrelation(torch.autograd.Function):
 
 
 def FunctionCorrelation(tensorFirst, tensorSecond):
+    if not (torch.is_grad_enabled() and (tensorFirst.requires_grad or tensorSecond.requires_grad)):
+        return _corr_forward(tensorFirst, tensorSecond)      # inference: nothing to record
     return _FunctionCorrelation.apply(tensorFirst, tensorSecond)
 
 
@@ -67,4 +74,4 @@ class ModuleCorrelation(torch.nn.Module):
         super(ModuleCorrelation, self).__init__()
 
     def forward(self, tensorFirst, tensorSecond):
-        return _FunctionCorrelation.apply(tensorFirst, tensorSecond)
+        return FunctionCorrelation(tensorFirst, tensorSecond)

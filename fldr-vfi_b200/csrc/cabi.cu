@@ -25,15 +25,16 @@ int sm_count() {
 }  // namespace fldr
 
 namespace fldr {
-static const char* const kOptionNames[kOptCount] = {"splat_stream", "splat_ring_mb", "splat_lag"};
-static const char* const kOptionEnv[kOptCount] = {"FLDR_SPLAT_STREAM", "FLDR_SPLAT_RING_MB", "FLDR_SPLAT_LAG"};
+static const char* const kOptionNames[kOptCount] = {"splat_stream", "splat_ring_mb", "splat_lag", "splat_fused_max"};
+static const char* const kOptionEnv[kOptCount] = {"FLDR_SPLAT_STREAM", "FLDR_SPLAT_RING_MB", "FLDR_SPLAT_LAG", "FLDR_SPLAT_FUSED_MAX"};
+static const int kOptionDefault[kOptCount] = {0, 0, 0, 40000};
 static int g_options[kOptCount];
 static bool g_options_init = false;
 static void init_options() {
     if (g_options_init) return;
     for (int i = 0; i < kOptCount; ++i) {
         const char* e = getenv(kOptionEnv[i]);
-        g_options[i] = e ? atoi(e) : 0;
+        g_options[i] = e ? atoi(e) : kOptionDefault[i];
     }
     g_options_init = true;
 }

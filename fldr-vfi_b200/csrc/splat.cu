@@ -13,7 +13,11 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace fldr {
 
@@ -566,6 +570,76 @@ __global__ void __launch_bounds__(256) splat_zero_kernel(float4* __restrict__ p,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Small frames: zero + scatter + normalise in ONE cooperative launch (two grid barriers instead of two kernel
+// boundaries and a memset).  The pyramid's small splats (C = 48 at 144x256 ... 18x32) are launch-latency bound:
+// three dependent launches cost ~20 us on an otherwise idle GPU, this costs ~8.
+// Phase B hands (plane, row run, 32-column block) units to warps; scatter_rows only needs warp-level convergence.
+// ------------------------------------------------------------------------------------------------
+template <int R, int WKIND, bool PRE>
+__global__ void __launch_bounds__(256) splat_fused_small_kernel(View4 in, View4 flow, View4 metric, float* __restrict__ acc,
+                                                                float* __restrict__ out, float* __restrict__ norm_out,
+                                                                SplatGeom g, int Q) {
+    cg::grid_group grid = cg::this_grid();
+    const long long HW = (long long)g.H * g.W;
+    const long long n4 = (long long)g.N * Q * HW;
+    const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long gthreads = (long long)gridDim.x * blockDim.x;
+    float4* acc4 = reinterpret_cast<float4*>(acc);
+    // ---- A: zero the accumulator
+    for (long long i = gtid; i < n4; i += gthreads) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    grid.sync();
+    // ---- B: scatter, one unit per warp
+    {
+        const int runs = (g.H + R - 1) / R, cblocks = (g.W + 31) / 32;
+        const long long units = (long long)g.N * Q * runs * cblocks;
+        const int lane = threadIdx.x & 31;
+        for (long long u = gtid >> 5; u < units; u += gthreads >> 5) {
+            const int cb = (int)(u % cblocks);
+            const int run = (int)((u / cblocks) % runs);
+            const int nq = (int)(u / ((long long)cblocks * runs));
+            const int q = nq % Q, n = nq / Q;
+            PlaneAcc pa;
+            pa.base = acc4 + (long long)nq * HW;
+            pa.W = g.W;
+            const int yb = run * R;
+            scatter_rows<WKIND, PRE, 0>(in, flow, metric, g, n, q, cb * 32 + lane, yb, min(R, g.H - yb), pa);
+        }
+    }
+    grid.sync();
+    // ---- C: normalise + post-scale + NCHW store (softSplat.py:343-349), one thread per (plane, pixel)
+    {
+        const bool has_norm = g.CA > g.C;
+        const int qn = g.C >> 2, slot = g.C & 3;
+        for (long long i = gtid; i < n4; i += gthreads) {
+            const long long pix = i % HW;
+            const int nq = (int)(i / HW);
+            const int q = nq % Q, n = nq / Q;
+            const float4 s4 = __ldcg(acc4 + i);
+            float d = 1.f;
+            if (has_norm) {
+                const float4 n4v = (qn == q) ? s4 : __ldcg(acc4 + ((long long)n * Q + qn) * HW + pix);
+                const float nrm = slot == 0 ? n4v.x : slot == 1 ? n4v.y : slot == 2 ? n4v.z : n4v.w;
+                if (norm_out && q == 0) norm_out[(long long)n * HW + pix] = nrm;
+                d = (nrm == 0.f) ? 1.f : nrm;
+            }
+            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+            float* op = out + (long long)n * g.C * HW + pix;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = q * 4 + j;
+                if (c < g.C) {
+                    float yv;
+                    if (g.mode == FLDR_SPLAT_RAW) yv = sv[j];
+                    else if (!has_norm) yv = (sv[j] - 0.5f) * 2.f;
+                    else yv = (sv[j] / d - 0.5f) * 2.f;
+                    op[(long long)c * HW] = yv;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Backward.  One thread per source pixel; gathers grad_out / forward output / normaliser at its 4 corners,
 // forms gS on the fly and emits grad_in, grad_flow, grad_metric in one pass:
 //   gS_c = 2 gY_c / norm'            gS_C = -sum_c gS_c * (S_c / norm')   (0 where norm was 0)
@@ -770,6 +844,35 @@ static int launch_whole_frame(const FwdPlan& p, const View4& vin, const View4& v
     int st;
     if ((long long)N * Q > 65535) return FLDR_ERR_UNSUPPORTED;
     const long long n4 = (long long)N * Q * H * W;
+    if (!guard && n4 <= (long long)get_option(kOptSplatFusedMax) && get_option(kOptSplatFusedMax) > 0) {
+        // small frame: single cooperative launch (zero / scatter / normalise separated by grid barriers)
+        const int wkind = !g.has_metric ? 0 : (g.mode == FLDR_SPLAT_SOFTMAX ? 1 : 2);
+        const bool pre = g.mode == FLDR_SPLAT_SOFTMAX;
+        const void* fn = wkind == 1 ? (const void*)splat_fused_small_kernel<4, 1, true>
+                       : wkind == 2 ? (const void*)splat_fused_small_kernel<4, 2, false>
+                       : pre        ? (const void*)splat_fused_small_kernel<4, 0, true>
+                                    : (const void*)splat_fused_small_kernel<4, 0, false>;
+        static int per_sm[4] = {0, 0, 0, 0};
+        const int slot = wkind == 1 ? 0 : wkind == 2 ? 1 : pre ? 2 : 3;
+        if (per_sm[slot] == 0) {
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, 256, 0) != cudaSuccess || nb < 1) nb = 1;
+            per_sm[slot] = nb;
+        }
+        const long long units = (long long)N * Q * ((H + 3) / 4) * ((W + 31) / 32);     // warps wanted in phase B
+        long long blocks = (units + 7) / 8;
+        const long long blocks_c = (n4 + 255) / 256;
+        if (blocks < blocks_c) blocks = blocks_c;
+        const long long cap = (long long)sm_count() * per_sm[slot];
+        if (blocks > cap) blocks = cap;
+        SplatGeom gg = g;
+        int QQ = Q;
+        View4 a0 = vin, a1 = vfl, a2 = vme;
+        void* args[] = {&a0, &a1, &a2, &acc, &out, &norm, &gg, &QQ};
+        cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(256), args, 0, s);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
+        return FLDR_OK;
+    }
     if (guard) {
         long long blocks = (n4 + 255) / 256;
         if (blocks > (long long)sm_count() * 8) blocks = (long long)sm_count() * 8;

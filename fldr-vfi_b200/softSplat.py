@@ -27,7 +27,9 @@ def _check_cuda_f32(name, t):
 
 
 def _stream_ptr(device):
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    # raw handle of the current stream at CALL time (softSplat.py:246); the C accessor is ~20x cheaper than
+    # torch.cuda.current_stream() and these ops are launch-latency bound on the small pyramid levels
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(device.index))
 
 
 class _device_of:
@@ -53,6 +55,18 @@ def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+_ws_bytes_cache = {}
+
+
+def _cached_ws_bytes(fn, *key):
+    """*_workspace_bytes depends on the shape only; remember it per shape (one ctypes call less per op call)."""
+    k = (fn.__name__,) + key
+    v = _ws_bytes_cache.get(k)
+    if v is None:
+        v = _ws_bytes_cache[k] = int(fn(*key))
+    return v
+
+
 def _splat_forward(mode, tenInput, tenFlow, tenMetric, want_norm):
     lib = _lib.lib()
     N, C, H, W = tenInput.shape
@@ -65,7 +79,7 @@ def _splat_forward(mode, tenInput, tenFlow, tenMetric, want_norm):
     metric = tenMetric
     if metric is not None:
         metric = metric.expand(N, 1, H, W)
-    ws_bytes = lib.fldr_splat_fwd_workspace_bytes(mode, N, C, H, W)
+    ws_bytes = _cached_ws_bytes(lib.fldr_splat_fwd_workspace_bytes, mode, N, C, H, W)
     ws = _workspace(ws_bytes, dev)
     with _device_of(tenInput):
         st = lib.fldr_splat_fwd(mode, _lib.ptr(tenInput), _lib.strides(tenInput), _lib.ptr(tenFlow),
@@ -85,7 +99,7 @@ def _splat_backward(mode, tenInput, tenFlow, tenMetric, out, norm, gradOutput, n
     metric = tenMetric
     if metric is not None:
         metric = metric.expand(N, 1, H, W)
-    ws_bytes = lib.fldr_splat_bwd_workspace_bytes(mode, N, C, H, W)
+    ws_bytes = _cached_ws_bytes(lib.fldr_splat_bwd_workspace_bytes, mode, N, C, H, W)
     ws = _workspace(ws_bytes, dev)
     with _device_of(tenInput):
         st = lib.fldr_splat_bwd(mode, _lib.ptr(tenInput), _lib.strides(tenInput), _lib.ptr(tenFlow),
@@ -154,7 +168,12 @@ def FunctionSoftsplat(tenInput, tenFlow, tenMetric, strType):
         _check_cuda_f32("tenMetric", tenMetric)
     if strType == 'linear' and tenMetric is None:
         raise TypeError("strType 'linear' needs tenMetric (softSplat.py:328)")
-    return _FusedSoftsplat.apply(tenInput, tenFlow, tenMetric, _lib.SPLAT_MODES[strType])
+    mode = _lib.SPLAT_MODES[strType]
+    if not (torch.is_grad_enabled() and (tenInput.requires_grad or tenFlow.requires_grad
+                                         or (tenMetric is not None and tenMetric.requires_grad))):
+        # inference (main.py:test runs under no_grad): nothing to record, skip the autograd.Function machinery
+        return _splat_forward(mode, tenInput, tenFlow, tenMetric, False)[0]
+    return _FusedSoftsplat.apply(tenInput, tenFlow, tenMetric, mode)
 
 
 class Softsplat(nn.Module):

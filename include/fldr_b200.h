@@ -66,6 +66,8 @@ int fldr_last_cuda_error(void);
  *                    ring accumulator (experimental)
  *   "splat_ring_mb"  ring size cap of the streaming kernel in MiB (0 = 32)
  *   "splat_lag"      schedule lag of the streaming kernel in strips (0 = automatic)
+ *   "splat_fused_max" frames with at most this many accumulator float4s (N * ceil((C+1)/4) * H * W, default 40000)
+ *                    run zero + scatter + normalise as ONE cooperative launch; 0 disables
  * Results are identical (within the summation-order tolerance) for every setting.
  */
 int fldr_set_option(const char* name, int value);
