@@ -3,6 +3,8 @@
 // Replaces OpticalFlow/correlation.py:17-242 (rearrange x2 + updateOutput; updateGradFirst / updateGradSecond
 // launched once per sample).  No NHWC scratch copies: tiles of the NCHW inputs are staged in shared memory
 // with their 4-pixel halo and zero fill, and every thread register-blocks 4 pixels x 3 dy x 9 dx.
+#include <string.h>
+
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -290,56 +292,142 @@ static int launch_fwd_tma(const View4& f1, const View4& f2, float* out, int B, i
 }
 
 // ------------------------------------------------------------------------------------------------
-// Backward (first version: one batched launch per gradient instead of the reference's launch per sample,
-// NCHW-coalesced stores, grad_out kept in registers across a chunk of channels).
-//   gF1[b,c,y,x] = (1/C) sum_{p,o} gOut[b,op,y,x]     * f2z[b,c,y+p,x+o]               (correlation.py:151-169)
-//   gF2[b,c,y,x] = (1/C) sum_{p,o} gOut[b,op,y-p,x-o] * f1 [b,c,y-p,x-o]  (in frame)   (correlation.py:200-236)
+// Backward.  Both gradients are the same tile computation
+//     G[b,c,y,x] = (1/C) sum_{p,o} A[b,(p,o),y,x] * Fz[b,c,y+p,x+o]          (Fz = F zero-extended)
+//   gradFirst : A = gradOut,  F = second                                        (correlation.py:151-169)
+//   gradSecond: A = G2,       F = first,  with  G2[(q,r)][y][x] = gradOut[(-q,-r)][y+q][x+r]  (0 out of frame)
+//               which is correlation.py:200-236 with the substitution q = -p, r = -o; G2 is plane 80-t of gradOut
+//               shifted by its own displacement, built by one elementwise pass into the workspace.
+// One batched launch per gradient (the reference: one launch per SAMPLE per gradient, correlation.py:365,385).
+// CTA = 32 x 8 pixels x 32 channels per pass, 256 threads = (4-pixel group, row, 8-channel group):
+//   the A tile [81][8][32] stays in shared memory for the whole tile, F is staged per 32-channel chunk with its halo;
+//   per displacement row p a thread loads 9 LDS.128 of A (its 4 pixels, 9 dx) once and 3 LDS.128 of F per channel,
+//   feeding 36 FFMA per channel into acc[8 channels][4 pixels].
 // ------------------------------------------------------------------------------------------------
-constexpr int kBwdChunk = 16;
+namespace bwd {
+constexpr int TW = 32, TH = 4, CK = 32, NT = 128;      // 2 CTAs per SM: one loads while the other computes
+constexpr int FH = TH + 2 * kPad, FW = TW + 2 * kPad;
+constexpr int A_FLOATS = 81 * TH * TW, F_FLOATS = CK * FH * FW;
+constexpr int SMEM_BYTES = (A_FLOATS + F_FLOATS) * 4 + 16;          // 41472 + 61440 + mbarrier
+}  // namespace bwd
 
-template <bool kSecond>
-__global__ void __launch_bounds__(128) corr81_bwd_kernel(View4 feat, View4 gout, float* __restrict__ grad, int C, int H,
-                                                         int W, int nchunks) {
-    const long long HW = (long long)H * W;
-    const long long per_b = HW * nchunks;
-    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (idx >= per_b) return;
-    const int x = (int)(idx % W);
-    const int y = (int)((idx / W) % H);
-    const int chunk = (int)(idx / HW);
-    const float* gp = gout.p + b * gout.sn;
-    const float* fp = feat.p + b * feat.sn;
-
-    float g[81];
-#pragma unroll
-    for (int p = 0; p < kD; ++p)
+// acc[8 channels][4 pixels] += sum over the 81 displacements, operands in shared memory
+__device__ __forceinline__ void bwd_tile_compute(const float* __restrict__ sA, const float* __restrict__ sF, int pg, int row,
+                                                 int cg, float (&acc)[8][4]) {
+    using namespace bwd;
+#pragma unroll 1
+    for (int p = 0; p < kD; ++p) {
+        float g[kD][4];
 #pragma unroll
         for (int o = 0; o < kD; ++o) {
-            // first: grad_out at (y, x); second: grad_out at the source pixel (y-p', x-o')
-            const int yy = kSecond ? y - (p - kPad) : y;
-            const int xx = kSecond ? x - (o - kPad) : x;
-            float v = 0.f;
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(gp + (p * kD + o) * gout.sc + yy * gout.sh + xx * gout.sw);
-            g[p * kD + o] = v;
+            const float4 g4 = *reinterpret_cast<const float4*>(sA + ((p * kD + o) * TH + row) * TW + pg * 4);
+            g[o][0] = g4.x; g[o][1] = g4.y; g[o][2] = g4.z; g[o][3] = g4.w;
         }
-    const float fc = (float)C;
-    const int c_end = min(C, (chunk + 1) * kBwdChunk);
-    for (int c = chunk * kBwdChunk; c < c_end; ++c) {
-        const float* fpc = fp + c * feat.sc;
-        float sum = 0.f;
 #pragma unroll
-        for (int p = 0; p < kD; ++p) {
-            const int yy = kSecond ? y - (p - kPad) : y + (p - kPad);
-            if (yy < 0 || yy >= H) continue;
+        for (int cc = 0; cc < 8; ++cc) {
+            const float4* rp = reinterpret_cast<const float4*>(sF + ((cg * 8 + cc) * FH + row + p) * FW + pg * 4);
+            const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
+            const float f[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
 #pragma unroll
-            for (int o = 0; o < kD; ++o) {
-                const int xx = kSecond ? x - (o - kPad) : x + (o - kPad);
-                if (xx >= 0 && xx < W) sum = fmaf(g[p * kD + o], __ldg(fpc + yy * feat.sh + xx * feat.sw), sum);
+            for (int o = 0; o < kD; ++o)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[cc][j] = fmaf(g[o][j], f[j + o], acc[cc][j]);
+        }
+    }
+}
+
+// TMA: A tile and F chunk arrive as two bulk tensor loads (zero fill outside the frame / beyond C) on one mbarrier
+template <bool TMA>
+__global__ void __launch_bounds__(bwd::NT, 2)
+corr81_bwd_tile_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmA, View4 F, View4 A,
+                       float* __restrict__ G, int C, int H, int W, float rc) {
+    using namespace bwd;
+    extern __shared__ __align__(128) float smem_f[];
+    float* sA = smem_f;                       // [81][TH][TW]
+    float* sF = smem_f + A_FLOATS;            // [CK][FH][FW]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_f + A_FLOATS + F_FLOATS);
+    const int tid = threadIdx.x;
+    const int pg = tid & 7, row = (tid >> 3) & 3, cg = tid >> 5;
+    const int x0t = blockIdx.x * TW, y0t = blockIdx.y * TH, b = blockIdx.z;
+    uint32_t phase = 0;
+    if (TMA) {
+        if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_arrive_expect_tx(bar, (A_FLOATS + F_FLOATS) * 4);
+            tma_load_4d(sA, &tmA, bar, x0t, y0t, 0, b);
+            tma_load_4d(sF, &tmF, bar, x0t - kPad, y0t - kPad, 0, b);
+        }
+    } else {
+        const float* pa = A.p + b * A.sn;
+        for (int e = tid; e < A_FLOATS; e += NT) {
+            const int t = e / (TH * TW), r = (e / TW) % TH, xx = e % TW;
+            const int gy = y0t + r, gx = x0t + xx;
+            sA[e] = (gy < H && gx < W) ? __ldg(pa + t * A.sc + gy * A.sh + gx * A.sw) : 0.f;
+        }
+    }
+    const int y = y0t + row, x = x0t + pg * 4;
+    const long long HW = (long long)H * W;
+    for (int c0 = 0; c0 < C; c0 += CK) {
+        if (TMA) {
+            if (c0 > 0) {
+                __syncthreads();                       // everyone is done reading the previous chunk
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(bar, F_FLOATS * 4);
+                    tma_load_4d(sF, &tmF, bar, x0t - kPad, y0t - kPad, c0, b);
+                }
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        } else {
+            const float* pf = F.p + b * F.sn;
+            __syncthreads();
+            for (int e = tid; e < F_FLOATS; e += NT) {
+                const int c = e / (FH * FW), r = (e / FW) % FH, xx = e % FW;
+                const int gy = y0t + r - kPad, gx = x0t + xx - kPad;
+                float v = 0.f;
+                if (c0 + c < C && gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(pf + (c0 + c) * F.sc + gy * F.sh + gx * F.sw);
+                sF[e] = v;
+            }
+            __syncthreads();
+        }
+        float acc[8][4];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[cc][j] = 0.f;
+        bwd_tile_compute(sA, sF, pg, row, cg, acc);
+        if (y < H && x < W) {
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                const int c = c0 + cg * 8 + cc;
+                if (c < C) {
+                    float* gp = G + ((long long)b * C + c) * HW + (long long)y * W + x;
+                    if ((W & 3) == 0) {
+                        __stcs(reinterpret_cast<float4*>(gp), make_float4(acc[cc][0] * rc, acc[cc][1] * rc, acc[cc][2] * rc, acc[cc][3] * rc));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (x + j < W) gp[j] = acc[cc][j] * rc;
+                    }
+                }
             }
         }
-        grad[((long long)b * C + c) * HW + (long long)y * W + x] = sum / fc;
     }
+}
+
+// G2[b][t'][y][x] = gradOut[b][80 - t'][y + q][x + r] for t' = (q+4)*9 + (r+4), zero when (y+q, x+r) leaves the frame
+__global__ void __launch_bounds__(256) corr81_bwd_shift_kernel(View4 gout, float* __restrict__ g2, int H, int W) {
+    const long long HW = (long long)H * W;
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= HW) return;
+    const int x = (int)(idx % W), y = (int)(idx / W);
+    const int t = blockIdx.y, b = blockIdx.z;
+    const int q = t / kD - kPad, r = t % kD - kPad;
+    const int yy = y + q, xx = x + r;
+    float v = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(gout.p + b * gout.sn + (80 - t) * gout.sc + yy * gout.sh + xx * gout.sw);
+    g2[((long long)b * 81 + t) * HW + idx] = v;
 }
 
 static int check_corr_args(int B, int C, int H, int W) {
@@ -382,32 +470,61 @@ extern "C" int fldr_corr81_fwd(const float* first, const int64_t* first_strides,
 }
 
 extern "C" size_t fldr_corr81_bwd_workspace_bytes(int B, int C, int H, int W) {
-    (void)B; (void)C; (void)H; (void)W;
-    return 0;
+    (void)C;
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return align_up((size_t)B * 81 * H * W * sizeof(float), 256);      // G2 for gradSecond
 }
 
 extern "C" int fldr_corr81_bwd(const float* first, const int64_t* first_strides, const float* second,
                                const int64_t* second_strides, const float* grad_out, const int64_t* grad_out_strides,
                                float* grad_first, float* grad_second, int B, int C, int H, int W, void* ws,
                                size_t ws_bytes, fldr_stream_t stream) {
-    (void)ws; (void)ws_bytes;
     int st = check_corr_args(B, C, H, W);
     if (st != FLDR_OK) return st;
     if (!first || !second || !first_strides || !second_strides || !grad_out || !grad_out_strides)
         return FLDR_ERR_INVALID_ARGUMENT;
+    if (grad_second && (!ws || ws_bytes < fldr_corr81_bwd_workspace_bytes(B, C, H, W))) return FLDR_ERR_WORKSPACE_TOO_SMALL;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const int nchunks = (C + kBwdChunk - 1) / kBwdChunk;
-    const long long per_b = (long long)H * W * nchunks;
-    dim3 grid((unsigned)((per_b + 127) / 128), B, 1);
+    const float rc = 1.0f / (float)C;
+    const View4 vg = make_view(grad_out, grad_out_strides);
+    const View4 v1 = make_view(first, first_strides), v2 = make_view(second, second_strides);
+    dim3 grid((W + bwd::TW - 1) / bwd::TW, (H + bwd::TH - 1) / bwd::TH, B);
+    const long long HW = (long long)H * W;
+    auto launch = [&](const View4& F, const View4& A, float* G) -> int {
+        CUtensorMap tmF, tmA;
+        const uint64_t dF[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)B};
+        const uint64_t dA[4] = {(uint64_t)W, (uint64_t)H, 81, (uint64_t)B};
+        const uint64_t sF[3] = {(uint64_t)F.sh * 4, (uint64_t)F.sc * 4, (uint64_t)F.sn * 4};
+        const uint64_t sA[3] = {(uint64_t)A.sh * 4, (uint64_t)A.sc * 4, (uint64_t)A.sn * 4};
+        const uint32_t bF[4] = {(uint32_t)bwd::FW, (uint32_t)bwd::FH, (uint32_t)bwd::CK, 1};
+        const uint32_t bA[4] = {(uint32_t)bwd::TW, (uint32_t)bwd::TH, 81, 1};
+        const bool strides_ok = (W % 4 == 0) && F.sw == 1 && A.sw == 1 && F.sh > 0 && F.sc > 0 && A.sh > 0 && A.sc > 0 &&
+                                (B == 1 || (F.sn > 0 && A.sn > 0));
+        const bool tma = strides_ok && encode_tensor_map_4d(&tmF, F.p, dF, sF, bF) && encode_tensor_map_4d(&tmA, A.p, dA, sA, bA);
+        cudaError_t e;
+        if (tma) {
+            e = cudaFuncSetAttribute(corr81_bwd_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES);
+            if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
+            corr81_bwd_tile_kernel<true><<<grid, bwd::NT, bwd::SMEM_BYTES, s>>>(tmF, tmA, F, A, G, C, H, W, rc);
+        } else {
+            memset(&tmF, 0, sizeof(tmF)); memset(&tmA, 0, sizeof(tmA));
+            e = cudaFuncSetAttribute(corr81_bwd_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES);
+            if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
+            corr81_bwd_tile_kernel<false><<<grid, bwd::NT, bwd::SMEM_BYTES, s>>>(tmF, tmA, F, A, G, C, H, W, rc);
+        }
+        return check_launch();
+    };
     if (grad_first) {
-        corr81_bwd_kernel<false><<<grid, 128, 0, s>>>(make_view(second, second_strides),
-                                                      make_view(grad_out, grad_out_strides), grad_first, C, H, W, nchunks);
-        if ((st = check_launch()) != FLDR_OK) return st;
+        if ((st = launch(v2, vg, grad_first)) != FLDR_OK) return st;
     }
     if (grad_second) {
-        corr81_bwd_kernel<true><<<grid, 128, 0, s>>>(make_view(first, first_strides),
-                                                     make_view(grad_out, grad_out_strides), grad_second, C, H, W, nchunks);
+        float* g2 = static_cast<float*>(ws);
+        dim3 sgrid((unsigned)((HW + 255) / 256), 81, B);
+        corr81_bwd_shift_kernel<<<sgrid, 256, 0, s>>>(vg, g2, H, W);
         if ((st = check_launch()) != FLDR_OK) return st;
+        View4 va;
+        va.p = g2; va.sn = 81 * HW; va.sc = HW; va.sh = W; va.sw = 1;
+        if ((st = launch(v1, va, grad_second)) != FLDR_OK) return st;
     }
     return FLDR_OK;
 }
