@@ -460,8 +460,12 @@ extern "C" int fldr_corr81_fwd(const float* first, const int64_t* first_strides,
     if (tma_ok) {
         bool used = false;
         const long long tiles16 = (long long)((W + 31) / 32) * ((H + 15) / 16) * B;
-        st = (tiles16 >= 2ll * sm_count()) ? launch_fwd_tma<16>(v1, v2, out, B, C, H, W, s, &used)
-                                           : launch_fwd_tma<8>(v1, v2, out, B, C, H, W, s, &used);
+        const int th_opt = get_option(kOptCorrTh);      // tuning hook: 0 = automatic, 8 or 16 forces the tile height
+        // measured (profiles/): two 8-row CTAs per SM overlap each other's epilogue / TMA-wait bubbles slightly better
+        // than one 16-row CTA (180 vs 187 us on the C = 32 level), so 8 is the default
+        const bool use16 = th_opt == 16;
+        (void)tiles16;
+        st = use16 ? launch_fwd_tma<16>(v1, v2, out, B, C, H, W, s, &used) : launch_fwd_tma<8>(v1, v2, out, B, C, H, W, s, &used);
         if (st != FLDR_OK || used) return st;
     }
     dim3 grid((W + fwd::TW - 1) / fwd::TW, (H + fwd::TH - 1) / fwd::TH, B);
