@@ -148,28 +148,31 @@ __device__ __forceinline__ bool scatter_rows(const View4& in, const View4& flow,
     float pw[4] = {0.f, 0.f, 0.f, 0.f};
     int px = kSentinel, py = kSentinel;
 
-    // software pipeline: the loads of row r+1 are issued before row r is processed
-    float nu = 0.f, nv = 0.f, nz = 0.f, nx[4] = {0.f, 0.f, 0.f, 0.f};
-    auto load = [&]() {
+    // software pipeline, two rows deep: the loads of rows r+1 and r+2 are in flight while row r is processed (the walk
+    // is serial per thread; ncu showed ~40 % of all stall samples on the first use of a just-loaded row with one row)
+    struct Row { float u, v, z, x[4]; };
+    auto load = [&](Row& L) {
+        L.u = 0.f; L.v = 0.f; L.z = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) L.x[j] = 0.f;
         if (inb) {
-            nu = __ldg(fu);
-            nv = __ldg(fv);
-            if (WKIND) nz = __ldg(zp);
+            L.u = __ldg(fu);
+            L.v = __ldg(fv);
+            if (WKIND) L.z = __ldg(zp);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (j < nch) nx[j] = __ldg(ip + (long long)j * in.sc);
+                if (j < nch) L.x[j] = __ldg(ip + (long long)j * in.sc);
         }
         fu += flow.sh; fv += flow.sh; ip += in.sh;
         if (WKIND) zp += metric.sh;
     };
-    if (rows > 0) load();
+    Row slot0, slot1;
+    if (rows > 0) load(slot0);
+    if (rows > 1) load(slot1);
 
-#pragma unroll 2
-    for (int r = 0; r < rows; ++r) {
-        const float u = nu, v = nv, z = nz;
-        const float xv[4] = {nx[0], nx[1], nx[2], nx[3]};
-        if (r + 1 < rows) load();
-
+    auto process = [&](const Row& L, int r) {
+        const float u = L.u, v = L.v, z = L.z;
+        const float xv[4] = {L.x[0], L.x[1], L.x[2], L.x[3]};
         // softSplat.py:23-38
         const float X = xf + u, Y = (float)(yb + r) + v;
         const float fx0 = floorf(X), fy0 = floorf(Y);
@@ -223,6 +226,17 @@ __device__ __forceinline__ bool scatter_rows(const View4& in, const View4& flow,
         px = x0; py = ok ? y0 + 1 : kSentinel;
 #pragma unroll
         for (int j = 0; j < 4; ++j) pw[j] = bW[j];
+    };
+
+    for (int r = 0; r < rows; r += 2) {
+        const Row c0 = slot0;
+        if (r + 2 < rows) load(slot0);
+        process(c0, r);
+        if (r + 1 < rows) {
+            const Row c1 = slot1;
+            if (r + 3 < rows) load(slot1);
+            process(c1, r + 1);
+        }
     }
     red4p(acc.at(px, py), pw, (unsigned)py < (unsigned)H && (unsigned)px < (unsigned)W);
     return overflow;
