@@ -55,6 +55,14 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(call):
+    """DRAM bytes per call of `call` from the committed ncu --set full capture (profiles/r1_traffic.json), or None."""
+    try:
+        return int(json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[call]["bytes"])
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------- inputs
 def make_pair_inputs(seed, frac=1.0):
     """Synthetic inputs of one 4K frame pair on the CPU: images seed+0, flow F1 seed+1,
@@ -122,7 +130,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.002)
 
     def start(self):
         if self.nv is not None:
@@ -254,7 +262,7 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic(dom), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": round(dom_ms, 4)},
             "breakdown": breakdown,
             "clocks": clk,
