@@ -105,12 +105,23 @@ struct PlaneAcc {          // whole-frame accumulator [H][W] float4
     int W;
     __device__ __forceinline__ float4* at(int x, int y) const { return base + (y * W + x); }
     __device__ __forceinline__ bool reachable(int) const { return true; }
+    // The whole-frame accumulator lives in DRAM; a reduction into a line that is not in L2 stalls the L2 reduction unit
+    // on the fill.  Pulling the target lines of the rows this thread will reach next into L2 ahead of time turns those
+    // fills into ordinary, well-pipelined reads.
+    int H, pf_rows;     // pf_rows: how many accumulator rows ahead of the row being scattered are pulled into L2
+    __device__ __forceinline__ int prefetch_rows() const { return pf_rows; }
+    __device__ __forceinline__ void prefetch(int x, int y) const {
+        if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (y * W + x)));
+    }
 };
 struct RingAcc {           // ring of RR rows (power of two): row y of sample n lives in slot row (row0 + y) & mask
     float4* base;          // plane of this quad: [RR][W] float4
     int W, row0, mask, ylo, yhi;
     __device__ __forceinline__ float4* at(int x, int y) const { return base + (((row0 + y) & mask) * W + x); }
     __device__ __forceinline__ bool reachable(int y0) const { return y0 >= ylo && y0 < yhi; }
+    __device__ __forceinline__ int prefetch_rows() const { return 0; }
+    __device__ __forceinline__ void prefetch(int, int) const {}       // the ring is L2-resident by construction
 };
 
 __device__ __forceinline__ void red4p(float4* d, const float* v, bool p) {
@@ -180,6 +191,11 @@ __device__ __forceinline__ bool scatter_rows(const View4& in, const View4& flow,
         if (ok && !acc.reachable((int)fy0)) { ok = false; overflow = true; }
         const int x0 = ok ? (int)fx0 : kSentinel;
         const int y0 = ok ? (int)fy0 : kSentinel;
+        if (ok && acc.prefetch_rows() > 0) {
+            if (r == 0)
+                for (int k = 0; k < acc.prefetch_rows(); ++k) acc.prefetch(x0, y0 + k);
+            acc.prefetch(x0, y0 + acc.prefetch_rows());
+        }
         const float ax = (fx0 + 1.f) - X, bx = X - fx0, ay = (fy0 + 1.f) - Y, by = Y - fy0;
         float m = 1.f;
         if (WKIND == 1) m = expf(z);          // accurate expf: the parity bar is 1e-5 relative
@@ -245,7 +261,7 @@ __device__ __forceinline__ bool scatter_rows(const View4& in, const View4& flow,
 template <int R, int WKIND, bool PRE, int QS>
 __global__ void __launch_bounds__(128) splat_scatter_merged_kernel(View4 in, View4 flow, View4 metric,
                                                                    float* __restrict__ acc, SplatGeom g, int Q,
-                                                                   const unsigned* __restrict__ guard) {
+                                                                   const unsigned* __restrict__ guard, int pf_rows) {
     if (guard && *guard == 0) return;      // fallback launch that turned out not to be needed
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int yb = blockIdx.y * R;
@@ -253,6 +269,8 @@ __global__ void __launch_bounds__(128) splat_scatter_merged_kernel(View4 in, Vie
     PlaneAcc pa;
     pa.base = reinterpret_cast<float4*>(acc) + (long long)(n * Q + q) * g.H * g.W;
     pa.W = g.W;
+    pa.H = g.H;
+    pa.pf_rows = pf_rows;
     scatter_rows<WKIND, PRE, QS>(in, flow, metric, g, n, q, x, yb, min(R, g.H - yb), pa);
 }
 
@@ -615,6 +633,8 @@ __global__ void __launch_bounds__(256) splat_fused_small_kernel(View4 in, View4 
             PlaneAcc pa;
             pa.base = acc4 + (long long)nq * HW;
             pa.W = g.W;
+            pa.H = g.H;
+            pa.pf_rows = 0;      // small frames: the accumulator is L2-resident anyway
             const int yb = run * R;
             scatter_rows<WKIND, PRE, 0>(in, flow, metric, g, n, q, cb * 32 + lane, yb, min(R, g.H - yb), pa);
         }
@@ -905,10 +925,13 @@ static int launch_whole_frame(const FwdPlan& p, const View4& vin, const View4& v
         const bool pre = g.mode == FLDR_SPLAT_SOFTMAX;
         // quad shape known at compile time for the image splat (C = 3 + weight) and for all-full-quad inputs
         const int qs = (g.C == 3 && g.CA == 4) ? 1 : (g.CA == g.C && g.C % 4 == 0) ? 2 : 0;
+        // accumulators larger than ~half the L2 are DRAM-resident when the reductions arrive: prefetch their lines
+        const int pf_opt = get_option(kOptSplatPfRows);
+        const int pf = ((size_t)n4 * 16 > (48u << 20)) ? (pf_opt > 0 ? pf_opt : (pf_opt < 0 ? 0 : 4)) : 0;
 #define FLDR_LAUNCH_SCATTER2(WK_, PRE_, QS_)                                                                             \
     do {                                                                                                                 \
-        if (small) splat_scatter_merged_kernel<4, WK_, PRE_, QS_><<<grid, bx, 0, s>>>(vin, vfl, vme, acc, g, Q, guard);   \
-        else splat_scatter_merged_kernel<16, WK_, PRE_, QS_><<<grid, bx, 0, s>>>(vin, vfl, vme, acc, g, Q, guard);        \
+        if (small) splat_scatter_merged_kernel<4, WK_, PRE_, QS_><<<grid, bx, 0, s>>>(vin, vfl, vme, acc, g, Q, guard, pf);   \
+        else splat_scatter_merged_kernel<16, WK_, PRE_, QS_><<<grid, bx, 0, s>>>(vin, vfl, vme, acc, g, Q, guard, pf);        \
     } while (0)
 #define FLDR_LAUNCH_SCATTER(WK_, PRE_)                                       \
     do {                                                                     \
