@@ -92,6 +92,12 @@ __device__ __forceinline__ float source_weight(const SplatGeom& g, const View4& 
 // ------------------------------------------------------------------------------------------------
 constexpr int kSentinel = -(1 << 28);
 
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 template <int PX> __device__ __forceinline__ void vstore(float* p, const float* t);
 template <> __device__ __forceinline__ void vstore<1>(float* p, const float* t) { __stcs(p, t[0]); }
 template <> __device__ __forceinline__ void vstore<4>(float* p, const float* t) {
@@ -114,6 +120,14 @@ struct PlaneAcc {          // whole-frame accumulator [H][W] float4
         if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (y * W + x)));
     }
+};
+struct BoundedPlaneAcc {   // whole-frame accumulator, but only rows [ylo, yhi) are known to be zeroed already (zero-ahead)
+    float4* base;
+    int W, ylo, yhi;
+    __device__ __forceinline__ float4* at(int x, int y) const { return base + (y * W + x); }
+    __device__ __forceinline__ bool reachable(int y0) const { return y0 >= ylo && y0 < yhi; }
+    __device__ __forceinline__ int prefetch_rows() const { return 0; }
+    __device__ __forceinline__ void prefetch(int, int) const {}
 };
 struct RingAcc {           // ring of RR rows (power of two): row y of sample n lives in slot row (row0 + y) & mask
     float4* base;          // plane of this quad: [RR][W] float4
@@ -167,12 +181,14 @@ __device__ __forceinline__ bool scatter_rows(const View4& in, const View4& flow,
 #pragma unroll
         for (int j = 0; j < 4; ++j) L.x[j] = 0.f;
         if (inb) {
-            L.u = __ldg(fu);
-            L.v = __ldg(fv);
-            if (WKIND) L.z = __ldg(zp);
+            // streaming (evict-first) loads: every input element is read exactly once and must not push the
+            // accumulator lines out of L2
+            L.u = __ldcs(fu);
+            L.v = __ldcs(fv);
+            if (WKIND) L.z = __ldcs(zp);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (j < nch) L.x[j] = __ldg(ip + (long long)j * in.sc);
+                if (j < nch) L.x[j] = __ldcs(ip + (long long)j * in.sc);
         }
         fu += flow.sh; fv += flow.sh; ip += in.sh;
         if (WKIND) zp += metric.sh;
@@ -272,6 +288,78 @@ __global__ void __launch_bounds__(128) splat_scatter_merged_kernel(View4 in, Vie
     pa.H = g.H;
     pa.pf_rows = pf_rows;
     scatter_rows<WKIND, PRE, QS>(in, flow, metric, g, n, q, x, yb, min(R, g.H - yb), pa);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pass 1 with zero-ahead (large frames).  The separate zero fill costs the accumulator two extra DRAM crossings: the
+// zeros are written out, and every line is fetched back when its first reduction arrives.  Here the scatter kernel
+// zeroes the accumulator itself, D strips AHEAD of the strip it scatters, so the reductions land on lines that are
+// still dirty-zero in L2 and the accumulator crosses DRAM once (write-back) instead of three times.
+//   * CTAs take tickets from an atomic counter (ticket order = strip order, column block fastest); the first tickets
+//     zero strips [0, D), every later ticket (G, c) first zeroes tile c of strip G + D, publishes it
+//     (__syncthreads, then thread 0: __threadfence + atomicAdd on zdone[G+D] - the cooperative-groups grid.sync
+//     pattern), then scatters tile c of strip G.
+//   * before scattering it waits (ld.acquire poll) until strips G-Rs-1 .. G+Rs+1 are completely zeroed; their zeroers
+//     hold lower tickets, so they are running or done: no deadlock, no co-residency assumption.
+//   * a source whose target row leaves that window sets ctrl[1]; the host-side sequence then re-does the call with
+//     the plain whole-frame path (guarded launches that exit at once otherwise).  Rs strips = +-128 rows by default.
+// ctrl (unsigned): [0] ticket counter, [1] overflow flag, [2 ..] zdone[global strip]
+// ------------------------------------------------------------------------------------------------
+template <int R, int WKIND, bool PRE, int QS>
+__global__ void __launch_bounds__(128) splat_scatter_za_kernel(View4 in, View4 flow, View4 metric, float* __restrict__ acc,
+                                                               SplatGeom g, int Q, unsigned* __restrict__ ctrl, int Tc,
+                                                               int NSr, int D, int Rs) {
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_ticket = (int)atomicAdd(&ctrl[0], 1u);
+    __syncthreads();
+    int k = s_ticket;
+    unsigned* zdone = ctrl + 2;
+    const int W = g.W, H = g.H;
+    const int total_strips = g.N * Q * NSr;
+    const int nz = min(D, total_strips) * Tc;          // leading zero-only tickets
+    float4* acc4 = reinterpret_cast<float4*>(acc);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    auto zero_tile = [&](int Gz, int c) {              // tile c of global strip Gz, then publish
+        const int plane = Gz / NSr, sz = Gz % NSr;
+        const int x = c * 128 + tid;
+        if (x < W) {
+            float4* p = acc4 + ((long long)plane * H + (long long)sz * R) * W + x;
+            const int rows = min(R, H - sz * R);
+#pragma unroll 4
+            for (int r = 0; r < rows; ++r) p[(long long)r * W] = zero4;
+        }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); atomicAdd(&zdone[Gz], 1u); }
+    };
+
+    if (k < nz) { zero_tile(k / Tc, k % Tc); return; }
+    k -= nz;
+    const int G = k / Tc, c = k % Tc;
+    if (G >= total_strips) return;
+    if (G + D < total_strips) zero_tile(G + D, c);
+    const int plane = G / NSr, sidx = G % NSr;
+    const int q = plane % Q, n = plane / Q;
+    const int slo = max(0, sidx - Rs - 1), shi = min(NSr - 1, sidx + Rs + 1);
+    if (tid < 32) {
+        for (;;) {
+            bool ready = true;
+            for (int ss = slo + tid; ss <= shi; ss += 32)
+                if (ld_acquire_u32(&zdone[plane * NSr + ss]) < (unsigned)Tc) ready = false;
+            if (__all_sync(0xffffffffu, ready)) break;
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    BoundedPlaneAcc pa;
+    pa.base = acc4 + (long long)plane * H * W;
+    pa.W = W;
+    pa.ylo = (slo == 0) ? -1 : slo * R;
+    pa.yhi = (shi == NSr - 1) ? H : (shi + 1) * R - 1;       // y0 + 1 must stay inside strip shi
+    const int yb = sidx * R;
+    const bool ovf = scatter_rows<WKIND, PRE, QS>(in, flow, metric, g, n, q, c * 128 + tid, yb, min(R, H - yb), pa);
+    if (__syncthreads_or(ovf) && tid == 0) atomicOr(&ctrl[1], 1u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -854,7 +942,11 @@ static int plan_fwd(int mode, int N, int C, int H, int W, bool has_metric, FwdPl
     sg.total = sg.nZ + sg.nA + sg.nB + (sg.NT - sg.jstart) * TQ;
     sg.vecN = 0;
     p.ring_bytes = align_up((size_t)rows * row_bytes, 256);
-    p.ctrl_bytes = align_up((size_t)(2 + sg.NT + sg.RS + (size_t)sg.NT * sg.T) * 4, 256);
+    {
+        const size_t stream_words = 2 + (size_t)sg.NT + sg.RS + (size_t)sg.NT * sg.T;
+        const size_t za_words = 2 + (size_t)N * sg.Q * ((H + 7) / 8);      // zero-ahead scatter: one counter per 8-row strip
+        p.ctrl_bytes = align_up((stream_words > za_words ? stream_words : za_words) * 4, 256);
+    }
     if (!p.stream_ok) { p.ring_bytes = 0; p.ctrl_bytes = 256; p.bounded = true; }
     p.total_bytes = p.ring_bytes + p.ctrl_bytes + (p.bounded ? p.full_bytes : 0);
     return FLDR_OK;
@@ -868,6 +960,22 @@ extern "C" size_t fldr_splat_fwd_workspace_bytes(int mode, int N, int C, int H, 
     FwdPlan p;
     if (plan_fwd(mode, N, C, H, W, true, p) != FLDR_OK) return 0;
     return p.total_bytes;
+}
+
+static int launch_normalise(const FwdPlan& p, float* acc, float* out, float* norm, const unsigned* guard, cudaStream_t s) {
+    const SplatGeom& g = p.g;
+    const int N = g.N, Q = p.sg.Q;
+    const long long HW = (long long)g.H * g.W;
+    const bool px4 = (HW % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                     (!norm || (reinterpret_cast<uintptr_t>(norm) & 15) == 0);
+    if (px4) {
+        dim3 grid((unsigned)((HW / 4 + 255) / 256), N * Q, 1);
+        splat_normalise_kernel<4><<<grid, 256, 0, s>>>(acc, out, norm, g, Q, guard);
+    } else {
+        dim3 grid((unsigned)((HW + 255) / 256), N * Q, 1);
+        splat_normalise_kernel<1><<<grid, 256, 0, s>>>(acc, out, norm, g, Q, guard);
+    }
+    return check_launch();
 }
 
 // whole-frame path: zero + merged scatter + normalise.  `guard` (device flag) makes the three launches no-ops unless set.
@@ -947,19 +1055,7 @@ static int launch_whole_frame(const FwdPlan& p, const View4& vin, const View4& v
 #undef FLDR_LAUNCH_SCATTER
     }
     if ((st = check_launch()) != FLDR_OK) return st;
-    {
-        const long long HW = (long long)H * W;
-        const bool px4 = (HW % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-                         (!norm || (reinterpret_cast<uintptr_t>(norm) & 15) == 0);
-        if (px4) {
-            dim3 grid((unsigned)((HW / 4 + 255) / 256), N * Q, 1);
-            splat_normalise_kernel<4><<<grid, 256, 0, s>>>(acc, out, norm, g, Q, guard);
-        } else {
-            dim3 grid((unsigned)((HW + 255) / 256), N * Q, 1);
-            splat_normalise_kernel<1><<<grid, 256, 0, s>>>(acc, out, norm, g, Q, guard);
-        }
-    }
-    return check_launch();
+    return launch_normalise(p, acc, out, norm, guard, s);
 }
 
 extern "C" int fldr_splat_fwd(int mode, const float* in, const int64_t* in_strides, const float* flow,
@@ -986,8 +1082,48 @@ extern "C" int fldr_splat_fwd(int mode, const float* in, const int64_t* in_strid
     // of the 4K image splat from 943 MB to 349 MB but, at ~215 us against ~205 us, does not yet beat the three-pass
     // sequence, and its L2-sized ring bounds the vertical flow it can take without the fallback.
     // whole-frame accumulator: behind ring + ctrl when the plan is bounded, else the (frame-sized) ring region itself
-    if (!p.stream_ok || get_option(kOptSplatStream) == 0)
-        return launch_whole_frame(p, vin, vfl, vme, p.bounded ? full : reinterpret_cast<float*>(ring), out, norm, nullptr, s);
+    if (!p.stream_ok || get_option(kOptSplatStream) == 0) {
+        float* acc = p.bounded ? full : reinterpret_cast<float*>(ring);
+        const long long n4 = (long long)N * p.sg.Q * H * W;
+        // Zero-ahead scatter (opt-in: "splat_za" = 8 or 16 rows per strip).  It removes the separate zero fill and most
+        // of the accumulator re-fetch (DRAM 640 -> 482 MB for the 4K image scatter) but its per-CTA hand-shake
+        // (ticket, zero tile + publish, poll) costs as much as it saves: 146 us vs 27 + 111 us (profiles/).
+        const int za = get_option(kOptSplatZa);
+        if ((za == 8 || za == 16) && (size_t)n4 * 16 > (48u << 20) && p.stream_ok && H >= 256) {
+            const int R = (za == 16) ? 16 : 8;
+            const int Tc = (W + 127) / 128;
+            const int NSr = (H + R - 1) / R;
+            const int Rs = 128 / R;                                     // +-128 rows of vertical reach
+            const int span = (sm_count() * 8 + Tc - 1) / Tc;            // strips covered by the resident CTAs
+            const int D = Rs + 1 + span + 4;
+            const long long total_strips = (long long)N * p.sg.Q * NSr;
+            const long long tickets = (total_strips < D ? total_strips : D) * Tc + total_strips * Tc;
+            if (tickets < (1ll << 31)) {
+                cudaError_t e = cudaMemsetAsync(ctrl, 0, p.ctrl_bytes, s);
+                if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
+                const int wkind = !g.has_metric ? 0 : (g.mode == FLDR_SPLAT_SOFTMAX ? 1 : 2);
+                const bool pre = g.mode == FLDR_SPLAT_SOFTMAX;
+                const int qs = (g.C == 3 && g.CA == 4) ? 1 : (g.CA == g.C && g.C % 4 == 0) ? 2 : 0;
+                const int Q = p.sg.Q;
+#define FLDR_LAUNCH_ZA3(R_, WK_, PRE_, QS_) \
+    splat_scatter_za_kernel<R_, WK_, PRE_, QS_><<<(unsigned)tickets, 128, 0, s>>>(vin, vfl, vme, acc, g, Q, ctrl, Tc, NSr, D, Rs)
+#define FLDR_LAUNCH_ZA2(WK_, PRE_, QS_) do { if (R == 16) FLDR_LAUNCH_ZA3(16, WK_, PRE_, QS_); else FLDR_LAUNCH_ZA3(8, WK_, PRE_, QS_); } while (0)
+#define FLDR_LAUNCH_ZA(WK_, PRE_) do { if (qs == 1) FLDR_LAUNCH_ZA2(WK_, PRE_, 1); else if (qs == 2) FLDR_LAUNCH_ZA2(WK_, PRE_, 2); else FLDR_LAUNCH_ZA2(WK_, PRE_, 0); } while (0)
+                if (wkind == 1) FLDR_LAUNCH_ZA(1, true);
+                else if (wkind == 2) FLDR_LAUNCH_ZA(2, false);
+                else if (pre) FLDR_LAUNCH_ZA(0, true);
+                else FLDR_LAUNCH_ZA(0, false);
+#undef FLDR_LAUNCH_ZA
+#undef FLDR_LAUNCH_ZA2
+#undef FLDR_LAUNCH_ZA3
+                if ((st = check_launch()) != FLDR_OK) return st;
+                if ((st = launch_normalise(p, acc, out, norm, nullptr, s)) != FLDR_OK) return st;
+                // bounded reach: arm the plain path; its launches exit at once unless the scatter flagged an overflow
+                return launch_whole_frame(p, vin, vfl, vme, acc, out, norm, ctrl + 1, s);
+            }
+        }
+        return launch_whole_frame(p, vin, vfl, vme, acc, out, norm, nullptr, s);
+    }
 
     cudaError_t e = cudaMemsetAsync(ctrl, 0, p.ctrl_bytes, s);
     if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }

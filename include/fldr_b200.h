@@ -69,6 +69,8 @@ int fldr_last_cuda_error(void);
  *   "splat_fused_max" frames with at most this many accumulator float4s (N * ceil((C+1)/4) * H * W, default 40000)
  *                    run zero + scatter + normalise as ONE cooperative launch; 0 disables
  *   "corr_th"        tile height of the correlation forward kernel: 0 automatic, 8 or 16 forced
+ *   "splat_za"       8 or 16: zero-ahead scatter for DRAM-resident accumulators with that strip height (experimental;
+ *                    0 = off, default)
  *   "splat_pf_rows"  accumulator rows prefetched into L2 ahead of the scatter (0 = default 4, negative = off)
  * Results are identical (within the summation-order tolerance) for every setting.
  */

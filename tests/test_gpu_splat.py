@@ -279,3 +279,44 @@ def test_batched_tall_frames_stream(cuda_lib, streaming):
     assert_splat_close(grads[0], gi, "batched tall grad_input", cond=gi - gi64)
     assert_splat_close(grads[1], gf, "batched tall grad_flow", cond=gf - gf64)
     assert_splat_close(grads[2], gz, "batched tall grad_metric", cond=gz - gz64)
+
+
+@pytest.fixture
+def zero_ahead(cuda_lib):
+    """Opt into the zero-ahead scatter for one test."""
+    cuda_lib.fldr_set_option(b"splat_za", 8)
+    yield
+    cuda_lib.fldr_set_option(b"splat_za", 0)
+
+
+def test_zero_ahead_scatter_overflow_falls_back(cuda_lib, zero_ahead):
+    """Opt-in path for DRAM-resident accumulators: the scatter kernel zeroes the accumulator a bounded distance ahead
+    of itself; a flow beyond that reach must flag the overflow on the device and re-do the call with the plain
+    whole-frame path (no host sync) - same result.  Also the in-reach case and zero-ahead switched off, for contrast."""
+    S = _mods(cuda_lib)
+    H, W = 1152, 4096
+    x = synth.image(1, 3, H, W, seed=81)
+    z = synth.metric(1, H, W, seed=82)
+    fl = synth.flow(1, H, W, "F1", seed=83)
+    fl[:, 1, 300:340, 1000:1400] += 260.0      # 260 rows down: beyond the +-128-row reach
+    fl[:, 1, 900:930, 2000:2100] -= 400.0      # 400 rows up
+    ref = so.function_softsplat(x, fl, z, "softmax")
+    y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), z.cuda(), "softmax")
+    assert_splat_close(y, ref, "zero-ahead overflow fallback", mag=1.0)
+    fl2 = synth.flow(1, H, W, "F1", seed=84)
+    fl2[:, 1, 300:340, 1000:1400] += 100.0
+    ref2 = so.function_softsplat(x, fl2, z, "softmax")
+    assert_splat_close(S.FunctionSoftsplat(x.cuda(), fl2.cuda(), z.cuda(), "softmax"), ref2, "zero-ahead in reach", mag=1.0)
+    cuda_lib.fldr_set_option(b"splat_za", 16)
+    assert_splat_close(S.FunctionSoftsplat(x.cuda(), fl2.cuda(), z.cuda(), "softmax"), ref2, "zero-ahead 16-row strips", mag=1.0)
+
+
+def test_zero_ahead_batched_multi_quad(cuda_lib, zero_ahead):
+    """Zero-ahead across plane boundaries: N = 2 samples x 2 channel quads (C = 6 + weight), tall frames."""
+    S = _mods(cuda_lib)
+    N, C, H, W = 2, 6, 640, 2048
+    x = synth.features(N, C, H, W, seed=95)
+    fl = synth.flow(N, H, W, "F1", seed=96) * 2
+    z = synth.metric(N, H, W, seed=97)
+    y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), z.cuda(), "softmax")
+    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "zero-ahead batched multi-quad", mag=1.0)
