@@ -136,7 +136,7 @@ corr81_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_cons
     constexpr int NWARPS = K::NT / 32;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWARPS); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         fence_barrier_init();
         tma_prefetch_desc(&tm1);
         tma_prefetch_desc(&tm2);
@@ -154,39 +154,44 @@ corr81_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_cons
         c_end = min(nchunks_all, c_begin + chunks_per_split);
     };
 
-    // producer cursor (thread 0 only) lives in shared memory: it must not cost the 383 consumer threads registers
-    __shared__ int ps[6];        // [0] item (local index), [1] tile, [2] chunk end, [3] next chunk, [4] chunks issued
+    // Refill protocol: the LAST warp to finish a chunk refills the stage it just freed with the chunk STAGES ahead.
+    // No warp ever waits for an "empty" signal and no fixed producer thread sits on the critical path; the cursor of
+    // the next chunk to issue lives in shared memory (refills happen in chunk order: the last finisher of chunk g+1
+    // cannot precede the last finisher of chunk g), so it costs the consumers no registers.
+    __shared__ volatile int ps[8];   // [0] item (local index), [1] tx, [2] ty, [3] b, [4] chunk end, [5] next chunk
+    __shared__ int done_cnt[STAGES];
     if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) done_cnt[s] = 0;
         int tile = 0, cb = 0, ce = 0;
         if (my_items > 0) item_chunks(blockIdx.x, tile, cb, ce);
-        ps[0] = 0; ps[1] = tile; ps[2] = ce; ps[3] = cb; ps[4] = 0;
+        ps[0] = 0; ps[1] = tile % tilesX; ps[2] = (tile / tilesX) % tilesY; ps[3] = tile / (tilesX * tilesY);
+        ps[4] = ce; ps[5] = cb;
     }
-    auto issue_next = [&]() {     // thread 0 only
+    auto issue_into = [&](int st) {     // one thread at a time
         const int il = ps[0];
         if (il >= my_items) return;
-        const int tile = ps[1], ch = ps[3], prod = ps[4];
-        const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, b = tile / (tilesX * tilesY);
-        const int st = prod % STAGES;
-        if (prod >= STAGES) mbar_wait(&empty[st], (uint32_t)((prod / STAGES - 1) & 1));
+        const int tx = ps[1], ty = ps[2], b = ps[3], ch = ps[5];
         float* s1 = reinterpret_cast<float*>(smem_raw + st * K::STAGE_BYTES);
         float* s2 = s1 + K::S1;
+        fence_proxy_async();            // the generic-proxy reads of this stage are ordered before the async-proxy refill
         mbar_arrive_expect_tx(&full[st], K::STAGE_BYTES);
         tma_load_4d(s1, &tm1, &full[st], tx * TW, ty * TH, ch * CK, b);
         tma_load_4d(s2, &tm2, &full[st], tx * TW - kPad, ty * TH - kPad, ch * CK, b);
-        ps[4] = prod + 1;
-        if (ch + 1 >= ps[2]) {
+        if (ch + 1 >= ps[4]) {
             ps[0] = il + 1;
             if (il + 1 < my_items) {
                 int ntile, cb, ce;
                 item_chunks(blockIdx.x + (il + 1) * gridDim.x, ntile, cb, ce);
-                ps[1] = ntile; ps[2] = ce; ps[3] = cb;
+                ps[1] = ntile % tilesX; ps[2] = (ntile / tilesX) % tilesY; ps[3] = ntile / (tilesX * tilesY);
+                ps[4] = ce; ps[5] = cb;
             }
         } else {
-            ps[3] = ch + 1;
+            ps[5] = ch + 1;
         }
     };
     if (tid == 0)
-        for (int i = 0; i < STAGES - 1; ++i) issue_next();
+        for (int i = 0; i < STAGES; ++i) issue_into(i);
+    __syncthreads();
 
     const float rc = 1.0f / (float)C;
     const long long HW = (long long)H * W;
@@ -203,7 +208,6 @@ corr81_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_cons
                 for (int j = 0; j < 4; ++j) acc[d][o][j] = 0.f;
 
         for (int ch = c_begin; ch < c_end; ++ch, ++g) {
-            if (tid == 0) issue_next();
             const int st = (int)(g % STAGES);
             mbar_wait(&full[st], (uint32_t)((g / STAGES) & 1));
             const float* s1 = reinterpret_cast<const float*>(smem_raw + st * K::STAGE_BYTES);
@@ -226,7 +230,13 @@ corr81_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_cons
                 }
             }
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+            if ((tid & 31) == 0) {
+                if (atomicAdd(&done_cnt[st], 1) == NWARPS - 1) {     // last warp out refills this stage
+                    done_cnt[st] = 0;
+                    __threadfence_block();
+                    issue_into(st);
+                }
+            }
         }
 
         const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, b = tile / (tilesX * tilesY);

@@ -44,6 +44,17 @@ def test_status_strings_and_version(lib):
     assert lib.fldr_status_string(-99) == b"FLDR_ERR_UNKNOWN"
 
 
+def test_options_roundtrip(lib):
+    """fldr_set_option / fldr_get_option: every documented switch exists, unknown names are rejected."""
+    for name in (b"splat_stream", b"splat_ring_mb", b"splat_lag", b"splat_fused_max", b"corr_th", b"splat_pf_rows", b"splat_za"):
+        old = lib.fldr_get_option(name)
+        assert lib.fldr_set_option(name, 7) == 0 and lib.fldr_get_option(name) == 7
+        assert lib.fldr_set_option(name, old) == 0
+    assert lib.fldr_set_option(b"no_such_option", 1) == -1
+    assert lib.fldr_set_option(None, 1) == -1
+    assert lib.fldr_get_option(b"no_such_option") == 0
+
+
 def test_workspace_sizes(lib):
     # 4K image splat: 512-row L2 ring + control words + whole-frame fallback accumulator (bounded reach)
     ring = 512 * 4096 * 16
