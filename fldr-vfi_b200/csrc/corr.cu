@@ -214,7 +214,7 @@ corr81_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_cons
             const float* s2 = s1 + K::S1;
             const float* p1 = s1 + row * TW + pg * 4;
             const float* p2 = s2 + (row + dyg * 3) * K::F2W + pg * 4;
-#pragma unroll 2
+#pragma unroll 4
             for (int c = 0; c < CK; ++c) {
                 const float4 a4 = *reinterpret_cast<const float4*>(p1 + c * (TH * TW));
                 const float a[4] = {a4.x, a4.y, a4.z, a4.w};
