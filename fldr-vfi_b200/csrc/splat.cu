@@ -274,10 +274,10 @@ __device__ __forceinline__ bool scatter_rows(const View4& in, const View4& flow,
     return overflow;
 }
 
-template <int R, int WKIND, bool PRE, int QS>
+template <int WKIND, bool PRE, int QS>
 __global__ void __launch_bounds__(128) splat_scatter_merged_kernel(View4 in, View4 flow, View4 metric,
                                                                    float* __restrict__ acc, SplatGeom g, int Q,
-                                                                   const unsigned* __restrict__ guard, int pf_rows) {
+                                                                   const unsigned* __restrict__ guard, int pf_rows, int R) {
     if (guard && *guard == 0) return;      // fallback launch that turned out not to be needed
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int yb = blockIdx.y * R;
@@ -392,6 +392,9 @@ __global__ void __launch_bounds__(256) splat_normalise_kernel(const float* __res
             const float4 n4 = (qn == q) ? s4[k] : __ldcs(accn + qn * HW + pix + k);
             nrm[k] = slot == 0 ? n4.x : slot == 1 ? n4.y : slot == 2 ? n4.z : n4.w;
             d[k] = (nrm[k] == 0.f) ? 1.f : nrm[k];
+            // many-channel frames (Q > 1: the C = 48 feature splats) are instruction-bound here: one IEEE reciprocal
+            // per pixel instead of one division per channel; S * (1/norm) is within 2 ulp of the reference's S / norm
+            if (Q > 1) d[k] = __frcp_rn(d[k]);
         }
         if (norm_out && q == 0) vstore<PX>(norm_out + (long long)n * HW + pix, nrm);
     }
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__(256) splat_normalise_kernel(const float* __res
                 const float sv = j == 0 ? s4[k].x : j == 1 ? s4[k].y : j == 2 ? s4[k].z : s4[k].w;
                 if (g.mode == FLDR_SPLAT_RAW) yv[k] = sv;
                 else if (!has_norm) yv[k] = (sv - 0.5f) * 2.f;
-                else yv[k] = (sv / d[k] - 0.5f) * 2.f;
+                else yv[k] = ((Q > 1 ? sv * d[k] : sv / d[k]) - 0.5f) * 2.f;
             }
             vstore<PX>(op + (long long)c * HW, yv);
         }
@@ -1025,10 +1028,14 @@ static int launch_whole_frame(const FwdPlan& p, const View4& vin, const View4& v
         if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
     }
     {
-        // small frames: short row runs and narrow blocks keep enough CTAs in flight; large frames: 16-row runs
-        const bool small = (long long)H * W * Q * N < 512 * 1024;
+        // rows walked per thread: 16 merges best vertically, but the walk is serial - shorten it until the grid offers
+        // at least two waves of CTAs (8 x 128 threads per SM)
         const int bx = W >= 128 ? 128 : ((W + 31) / 32) * 32;
-        dim3 grid((W + bx - 1) / bx, small ? (H + 3) / 4 : (H + 15) / 16, N * Q);
+        const long long per_row_ctas = (long long)((W + bx - 1) / bx) * N * Q;
+        const long long two_waves = 2ll * sm_count() * 8;
+        int R = 16;
+        while (R > 4 && per_row_ctas * ((H + R - 1) / R) < two_waves) R >>= 1;
+        dim3 grid((W + bx - 1) / bx, (H + R - 1) / R, N * Q);
         const int wkind = !g.has_metric ? 0 : (g.mode == FLDR_SPLAT_SOFTMAX ? 1 : 2);
         const bool pre = g.mode == FLDR_SPLAT_SOFTMAX;
         // quad shape known at compile time for the image splat (C = 3 + weight) and for all-full-quad inputs
@@ -1036,11 +1043,8 @@ static int launch_whole_frame(const FwdPlan& p, const View4& vin, const View4& v
         // accumulators larger than ~half the L2 are DRAM-resident when the reductions arrive: prefetch their lines
         const int pf_opt = get_option(kOptSplatPfRows);
         const int pf = ((size_t)n4 * 16 > (48u << 20)) ? (pf_opt > 0 ? pf_opt : (pf_opt < 0 ? 0 : 4)) : 0;
-#define FLDR_LAUNCH_SCATTER2(WK_, PRE_, QS_)                                                                             \
-    do {                                                                                                                 \
-        if (small) splat_scatter_merged_kernel<4, WK_, PRE_, QS_><<<grid, bx, 0, s>>>(vin, vfl, vme, acc, g, Q, guard, pf);   \
-        else splat_scatter_merged_kernel<16, WK_, PRE_, QS_><<<grid, bx, 0, s>>>(vin, vfl, vme, acc, g, Q, guard, pf);        \
-    } while (0)
+#define FLDR_LAUNCH_SCATTER2(WK_, PRE_, QS_) \
+    splat_scatter_merged_kernel<WK_, PRE_, QS_><<<grid, bx, 0, s>>>(vin, vfl, vme, acc, g, Q, guard, pf, R)
 #define FLDR_LAUNCH_SCATTER(WK_, PRE_)                                       \
     do {                                                                     \
         if (qs == 1) FLDR_LAUNCH_SCATTER2(WK_, PRE_, 1);                     \
