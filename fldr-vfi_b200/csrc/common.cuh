@@ -41,14 +41,4 @@ int get_option(int opt);
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
-}
-__device__ __forceinline__ void red_add(float* addr, float a) {
-    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
-}
-
-// streaming loads / stores: inputs are read once, outputs written once
-__device__ __forceinline__ float ld_stream(const float* p) { return __ldg(p); }
-
 }  // namespace fldr

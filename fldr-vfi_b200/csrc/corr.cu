@@ -1,8 +1,13 @@
 // PWC-Net 9x9 cost volume (81 displacements, zero padding 4, mean over channels), forward + backward, sm_100a.
 //
 // Replaces OpticalFlow/correlation.py:17-242 (rearrange x2 + updateOutput; updateGradFirst / updateGradSecond
-// launched once per sample).  No NHWC scratch copies: tiles of the NCHW inputs are staged in shared memory
-// with their 4-pixel halo and zero fill, and every thread register-blocks 4 pixels x 3 dy x 9 dx.
+// launched once per sample).  No NHWC scratch copies: tiles of the NCHW inputs are staged in shared memory by TMA
+// with their 4-pixel halo (the TMA unit's out-of-bounds zero fill IS the reference's zero padding), and every thread
+// register-blocks 4 pixels x 3 dy x 9 dx (forward) or 8 channels x 4 pixels (backward).
+//   corr81_fwd_tma_kernel   persistent CTAs, 3-stage mbarrier ring refilled by the last warp out of a chunk;
+//                           channel-split + red.global.add.v4 for levels with fewer tiles than SMs
+//   corr81_fwd_kernel       plain-load fallback (W % 4 != 0, unaligned or exotic views)
+//   corr81_bwd_tile_kernel  both gradients (gradSecond through the shifted planes built by corr81_bwd_shift_kernel)
 #include <string.h>
 
 #include "common.cuh"

@@ -2,14 +2,21 @@
 //
 // Replaces softSplat.py:12-158 (three CuPy string kernels) AND the ~12 torch elementwise kernels
 // FunctionSoftsplat wraps around them (softSplat.py:320-352): pre-scale, exp, cat, zero-init,
-// normaliser fix-up, divide, post-scale are all folded into the two passes below.
+// normaliser fix-up, divide, post-scale are all folded into the passes below.
 //
 // Data layout in HBM
 //   inputs      NCHW fp32 with arbitrary element strides (callers pass views: fLDRnet.py:386,449)
-//   accumulator pixel-interleaved [N, H, W, CP] fp32, CP = round_up(C + has_norm, 4): one source pixel's
-//               whole payload for one corner is CP/4 red.global.add.v4.f32 requests (16 B each) instead
-//               of CP scalar REDs to CP planes (the reference issues 4 scalar REDs per element, 39-50).
+//   accumulator [N][Q][H][W][4] fp32, Q = ceil((C + has_norm) / 4): every channel quad is a pixel-interleaved
+//               float4 image, so one corner of one source pixel is ONE 16-byte red.global.add.v4.f32 and adjacent
+//               lanes (adjacent x) reduce into adjacent slots (the reference issues 4 scalar REDs per element,
+//               softSplat.py:39-50).  The normaliser rides in slot C % 4 of quad C / 4.
 //   outputs     NCHW contiguous (what the reference allocates, softSplat.py:234).
+//
+// Paths (fldr_splat_fwd picks; DESIGN.md section 4.1 has the measurements behind each choice)
+//   default        cudaMemsetAsync + splat_scatter_merged_kernel + splat_normalise_kernel
+//   tiny frames    splat_fused_small_kernel: the three phases in one cooperative launch
+//   opt-in         splat_scatter_za_kernel ("splat_za"): the scatter zeroes the accumulator ahead of itself
+//   opt-in         splat_stream_kernel ("splat_stream"): one launch, L2-resident ring accumulator, dataflow counters
 #include <math.h>
 #include <stdlib.h>
 
@@ -62,14 +69,6 @@ __device__ __forceinline__ bool make_corners(int x, int y, float u, float v, int
     k.valid[2] = xl && yb;
     k.valid[3] = xr && yb;
     return true;
-}
-
-__device__ __forceinline__ float source_weight(const SplatGeom& g, const View4& metric, int n, int y, int x) {
-    if (!g.has_metric) return 1.f;
-    const float z = __ldg(metric.p + n * metric.sn + y * metric.sh + x * metric.sw);
-    if (g.mode == FLDR_SPLAT_SOFTMAX) return expf(z);   // accurate expf: parity bar is 1e-5 relative
-    if (g.mode == FLDR_SPLAT_LINEAR) return z;
-    return 1.f;
 }
 
 // ------------------------------------------------------------------------------------------------
