@@ -26,6 +26,10 @@
 
 namespace cg = cooperative_groups;
 
+#ifndef FLDR_SCATTER_MIN_CTAS
+#define FLDR_SCATTER_MIN_CTAS 8
+#endif
+
 namespace fldr {
 
 struct SplatGeom {
@@ -274,7 +278,7 @@ __device__ __forceinline__ bool scatter_rows(const View4& in, const View4& flow,
 }
 
 template <int WKIND, bool PRE, int QS>
-__global__ void __launch_bounds__(128) splat_scatter_merged_kernel(View4 in, View4 flow, View4 metric,
+__global__ void __launch_bounds__(128, FLDR_SCATTER_MIN_CTAS) splat_scatter_merged_kernel(View4 in, View4 flow, View4 metric,
                                                                    float* __restrict__ acc, SplatGeom g, int Q,
                                                                    const unsigned* __restrict__ guard, int pf_rows, int R) {
     if (guard && *guard == 0) return;      // fallback launch that turned out not to be needed
