@@ -25,9 +25,9 @@ int sm_count() {
 }  // namespace fldr
 
 namespace fldr {
-static const char* const kOptionNames[kOptCount] = {"splat_stream", "splat_ring_mb", "splat_lag", "splat_fused_max", "corr_th", "splat_pf_rows", "splat_za"};
-static const char* const kOptionEnv[kOptCount] = {"FLDR_SPLAT_STREAM", "FLDR_SPLAT_RING_MB", "FLDR_SPLAT_LAG", "FLDR_SPLAT_FUSED_MAX", "FLDR_CORR_TH", "FLDR_SPLAT_PF_ROWS", "FLDR_SPLAT_ZA"};
-static const int kOptionDefault[kOptCount] = {0, 0, 0, 40000, 0, 0, 0};
+static const char* const kOptionNames[kOptCount] = {"splat_stream", "splat_ring_mb", "splat_lag", "splat_fused_max", "corr_th", "splat_pf_rows", "splat_za", "splat_l2_persist"};
+static const char* const kOptionEnv[kOptCount] = {"FLDR_SPLAT_STREAM", "FLDR_SPLAT_RING_MB", "FLDR_SPLAT_LAG", "FLDR_SPLAT_FUSED_MAX", "FLDR_CORR_TH", "FLDR_SPLAT_PF_ROWS", "FLDR_SPLAT_ZA", "FLDR_SPLAT_L2_PERSIST"};
+static const int kOptionDefault[kOptCount] = {0, 0, 0, 40000, 0, 0, 0, 0};
 static int g_options[kOptCount];
 static bool g_options_init = false;
 static void init_options() {

@@ -19,6 +19,7 @@
 //   opt-in         splat_stream_kernel ("splat_stream"): one launch, L2-resident ring accumulator, dataflow counters
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <cooperative_groups.h>
 
@@ -1147,6 +1148,20 @@ extern "C" int fldr_splat_fwd(int mode, const float* in, const int64_t* in_strid
         const int wkind = !g.has_metric ? 0 : (g.mode == FLDR_SPLAT_SOFTMAX ? 1 : 2);
         const bool pre = g.mode == FLDR_SPLAT_SOFTMAX;
         const int qs = (g.C == 3 && g.CA == 4) ? 1 : (g.CA == g.C && g.C % 4 == 0) ? 2 : 0;
+        // experiment hook ("splat_l2_persist" = 1): pin the ring in the persisting L2 carve-out for this launch
+        const bool persist = get_option(kOptSplatL2Persist) > 0;
+        if (persist) {
+            static bool limit_set = false;
+            if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)96 << 20); limit_set = true; }
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof(av));
+            av.accessPolicyWindow.base_ptr = ring;
+            av.accessPolicyWindow.num_bytes = p.ring_bytes;
+            av.accessPolicyWindow.hitRatio = 1.0f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
+        }
 #define FLDR_LAUNCH_STREAM2(WK_, PRE_, QS_) \
     splat_stream_kernel<WK_, PRE_, QS_><<<(unsigned)grid, stream::TWC, 0, s>>>(vin, vfl, vme, ring, ctrl, out, norm, g, p.sg)
 #define FLDR_LAUNCH_STREAM(WK_, PRE_)                        \
@@ -1161,6 +1176,11 @@ extern "C" int fldr_splat_fwd(int mode, const float* in, const int64_t* in_strid
         else FLDR_LAUNCH_STREAM(0, false);
 #undef FLDR_LAUNCH_STREAM2
 #undef FLDR_LAUNCH_STREAM
+        if (persist) {
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof(av));
+            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
+        }
         if ((st = check_launch()) != FLDR_OK) return st;
     }
     // bounded reach: arm the whole-frame path; its launches exit at once unless the streaming pass flagged an overflow

@@ -71,6 +71,7 @@ int fldr_last_cuda_error(void);
  *   "corr_th"        tile height of the correlation forward kernel: 0 automatic, 8 or 16 forced
  *   "splat_za"       8 or 16: zero-ahead scatter for DRAM-resident accumulators with that strip height (experimental;
  *                    0 = off, default)
+ *   "splat_l2_persist" 1: pin the streaming kernel's ring with a persisting-L2 access policy window (experiment)
  *   "splat_pf_rows"  accumulator rows prefetched into L2 ahead of the scatter (0 = default 4, negative = off)
  * Results are identical (within the summation-order tolerance) for every setting.
  */

@@ -46,7 +46,7 @@ def test_status_strings_and_version(lib):
 
 def test_options_roundtrip(lib):
     """fldr_set_option / fldr_get_option: every documented switch exists, unknown names are rejected."""
-    for name in (b"splat_stream", b"splat_ring_mb", b"splat_lag", b"splat_fused_max", b"corr_th", b"splat_pf_rows", b"splat_za"):
+    for name in (b"splat_stream", b"splat_ring_mb", b"splat_lag", b"splat_fused_max", b"corr_th", b"splat_pf_rows", b"splat_za", b"splat_l2_persist"):
         old = lib.fldr_get_option(name)
         assert lib.fldr_set_option(name, 7) == 0 and lib.fldr_get_option(name) == 7
         assert lib.fldr_set_option(name, old) == 0
