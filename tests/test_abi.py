@@ -80,6 +80,11 @@ def test_argument_validation_needs_no_device(lib):
     assert lib.fldr_splat_fwd(2, p, s4, p, s4, None, None, p, None, 1, 3, 8, 8, p, 1 << 20, None) == -4
     # workspace too small
     assert lib.fldr_splat_fwd(3, p, s4, p, s4, None, None, p, None, 1, 3, 8, 8, p, 16, None) == -2
+    # maximum sizes: planes of 2^31 pixels and more are refused up front, not mis-indexed (the reference's int32
+    # element index silently overflows there, softSplat.py:18-22)
+    assert lib.fldr_splat_fwd(3, p, s4, p, s4, None, None, p, None, 1, 3, 65536, 65536, p, 1 << 20, None) == -4
+    assert lib.fldr_splat_bwd(3, p, s4, p, s4, None, None, p, p, p, s4, p, None, None, 1, 3, 65536, 65536, None, 0, None) == -4
+    assert lib.fldr_corr81_fwd(p, s4, p, s4, p, 70000, 4, 8, 8, None, 0, None) == -4
     assert lib.fldr_corr81_fwd(None, s4, p, s4, p, 1, 4, 8, 8, None, 0, None) == -1
     assert lib.fldr_corr81_fwd(p, s4, p, s4, p, 0, 4, 8, 8, None, 0, None) == -1
     assert lib.fldr_corr81_bwd(p, s4, p, s4, None, s4, p, p, 1, 4, 8, 8, None, 0, None) == -1
