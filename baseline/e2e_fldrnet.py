@@ -46,7 +46,7 @@ def synthetic_triplet(H=2160, W=4096, seed=0):
 
 def worker(impl, out_path, reps, height, width):
     import torch
-    if impl == "ours":
+    if impl.startswith("ours"):
         sys.path.insert(0, os.path.join(ROOT, "fldr-vfi_b200", "dropin"))
     sys.path.insert(1, REFDIR)
     sys.path.append(os.path.join(HERE, "cupy_shim"))
@@ -62,6 +62,19 @@ def worker(impl, out_path, reps, height, width):
     import torch.nn.functional as F
     from torch.autograd import Variable
     which = os.path.abspath(softSplat.__file__)
+    if impl == "ours_warp":
+        # next row: replace the bwarp METHOD on the imported class - fLDRnet.py itself stays untouched
+        import fLDRnet
+        sys.path.insert(0, ROOT)
+        from fldr_vfi_b200.warp import bwarp as fast_bwarp
+        ref_bwarp = fLDRnet.DCTVFInet.bwarp
+
+        def patched(self, x, flo, withmask=True, minus=False):
+            if x.dtype != torch.float32 or flo.dtype != torch.float32 or not x.is_cuda or torch.is_grad_enabled():
+                return ref_bwarp(self, x, flo, withmask, minus)      # the reference's own path for what this row does not cover
+            return fast_bwarp(x, flo, withmask)
+        fLDRnet.DCTVFInet.bwarp = patched
+        which += " + fldr_vfi_b200.warp.bwarp"
     model_net, device, args = R.prepare_model()
     model_net.eval()
     frames = synthetic_triplet(height, width)
@@ -104,7 +117,7 @@ def worker(impl, out_path, reps, height, width):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--impl", default=None, choices=["ours", "reference"])
+    ap.add_argument("--impl", default=None, choices=["ours", "ours_warp", "reference"])
     ap.add_argument("--out", default=None)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--height", type=int, default=2160)
@@ -115,8 +128,8 @@ def main():
         return
     import torch
     res = {}
-    for tag in ("reference", "reference_again", "ours"):
-        impl = "reference" if tag.startswith("reference") else "ours"
+    for tag in ("reference", "reference_again", "ours", "ours_warp"):
+        impl = "reference" if tag.startswith("reference") else tag
         out = f"/tmp/fldr_e2e_{tag}.pt"
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", impl, "--out", out, "--reps", str(a.reps),
                             "--height", str(a.height), "--width", str(a.width)], capture_output=True, text=True)
@@ -137,6 +150,9 @@ def main():
         "reference_run_to_run_max_abs_diff": float(dr.max()), "reference_run_to_run_mean_abs_diff": float(dr.mean()),
         "model_forward_s": med, "frame_pairs_per_s": {k: 1.0 / v for k, v in med.items()},
         "e2e_speedup": med["reference"] / med["ours"],
+        "with_bwarp_row": {"psnr_dB": res["ours_warp"]["psnr"], "psnr_abs_diff_dB": abs(res["ours_warp"]["psnr"] - res["reference"]["psnr"]),
+                           "max_abs_output_diff": float((res["ours_warp"]["pred"] - res["reference"]["pred"]).abs().max()),
+                           "e2e_speedup": med["reference"] / med["ours_warp"]},
         "softSplat_module": {k: v["softSplat"] for k, v in res.items()}}))
 
 

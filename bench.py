@@ -355,6 +355,8 @@ def run_ours(args, rank, world, local_rank):
             "breakdown": breakdown,
             "clocks": clk,
         }
+        if world == 1:
+            line["next_rows"] = next_rows_probe(devin, peak)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(frac=1.0)
         if world == 1 and not args.no_ref_gpu:
@@ -365,6 +367,37 @@ def run_ours(args, rank, world, local_rank):
 
 
 # ----------------------------------------------------------------------------------------------- reference on the GPU
+def next_rows_probe(devin, peak):
+    """SURVEY.md 8f rank 1 (outside the step above, reported beside it): the backward warp and the splat metric that
+    fLDRnet runs just before the image splat (fLDRnet.py:442-446, 546-581), on this pair's 4K images and flows.
+    Inputs exceed the L2; CUDA events on the current stream; median of 20."""
+    import fldr_vfi_b200.warp as Wp
+    img = [t for n, t in devin if n == "splat_image"]
+    x0, x1, fl = img[0]["x"], img[1]["x"], img[0]["flow"]
+    N, C, H, W = x0.shape
+    px = N * H * W
+
+    def med(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(20):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    out = {}
+    with torch.no_grad():
+        for name, nbytes, fn in (("bwarp_image_C3", 4 * px * (C + 2 + C), lambda: Wp.bwarp(x1, fl, True)),
+                                 ("splat_metric_C3", 4 * px * (2 * C + 2 + 1), lambda: Wp.splat_metric(x0, x1, fl, -1.894))):
+            ms = med(fn)
+            out[name] = {"ms_per_call": round(ms, 4), "algorithmic_bytes": nbytes, "GBps": round(nbytes / ms / 1e6, 1),
+                         "frac_of_peak": round(nbytes / ms / 1e6 / peak, 3)}
+    return out
+
+
 def ref_gpu_baseline(devin, args):
     """The reference's own CuPy kernels on the same B200 (north_star's first reported baseline): the UNMODIFIED
     softSplat.py / OpticalFlow/correlation.py staged in baseline/_ref, CuPy replaced by an NVRTC shim

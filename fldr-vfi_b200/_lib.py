@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfldr_b200.so")
+LIB_PATH = os.environ.get("FLDR_B200_LIB") or os.path.join(_HERE, "libfldr_b200.so")     # override: A/B builds of the same ABI
 
 c_float_p = ctypes.c_void_p
 c_i64_p = ctypes.POINTER(ctypes.c_int64)
@@ -36,6 +36,11 @@ SYMBOLS = {
     "fldr_corr81_bwd": (ctypes.c_int, [c_float_p, c_i64_p, c_float_p, c_i64_p, c_float_p, c_i64_p,
                                        c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "fldr_bwarp_fwd": (ctypes.c_int, [c_float_p, c_i64_p, c_float_p, c_i64_p, c_float_p,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "fldr_warp_metric_fwd": (ctypes.c_int, [c_float_p, c_i64_p, c_float_p, c_i64_p, c_float_p, c_i64_p, ctypes.c_float,
+                                            c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_void_p]),
 }
 
 SPLAT_MODES = {"summation": 0, "average": 1, "linear": 2, "softmax": 3, "raw": 4}

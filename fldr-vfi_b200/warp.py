@@ -1,0 +1,59 @@
+"""Host mirror of fLDRnet's backward warp and splat metric over the sm_100a C-ABI library.
+
+Same call shapes as the reference (file:line = /root/reference/fLDRnet.py):
+
+  bwarp(x, flo, withmask=True)                         546-581   DCTVFInet.bwarp as a free function
+  splat_metric(x_ref, x_src, flo, z_alpha, withmask)   442-443   z = mean_c(z_alpha * |x_ref - bwarp(x_src, flo)|)
+
+``bwarp`` can replace the method without editing fLDRnet.py:  ``DCTVFInet.bwarp = lambda self, x, flo, withmask=True,
+minus=False: bwarp(x, flo, withmask)``.  Forward only in this round: tensors that require grad
+while grad mode is on raise instead of silently detaching (training keeps the reference's torch path).
+"""
+import torch
+
+from . import _lib
+from .softSplat import _check_cuda_f32, _device_of, _stream_ptr
+
+
+def _check_no_grad(*tensors):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError("fldr_b200 bwarp / splat_metric are forward-only: call under torch.no_grad() "
+                                  "(the backward of this row is not built yet)")
+
+
+def bwarp(x, flo, withmask=True):
+    """x [B,C,H,W], flo [B,2,H,W] -> x sampled at (p + flo) with the reference's normalisation, times the 0.999 mask."""
+    if not x.is_cuda:
+        raise NotImplementedError()
+    _check_cuda_f32("x", x)
+    _check_cuda_f32("flo", flo)
+    _check_no_grad(x, flo)
+    B, C, H, W = x.shape
+    assert flo.shape == (B, 2, H, W)
+    lib = _lib.lib()
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    with _device_of(x):
+        st = lib.fldr_bwarp_fwd(_lib.ptr(x), _lib.strides(x), _lib.ptr(flo), _lib.strides(flo), _lib.ptr(out),
+                                B, C, H, W, 1 if withmask else 0, _stream_ptr(x.device))
+    _lib.check(st)
+    return out
+
+
+def splat_metric(x_ref, x_src, flo, z_alpha, withmask=True):
+    """mean_c(z_alpha * |x_ref - bwarp(x_src, flo)|), keepdim -> [B,1,H,W]; ``z_alpha`` a Python number or 0-dim tensor."""
+    if not x_ref.is_cuda:
+        raise NotImplementedError()
+    _check_cuda_f32("x_ref", x_ref)
+    _check_cuda_f32("x_src", x_src)
+    _check_cuda_f32("flo", flo)
+    _check_no_grad(x_ref, x_src, flo, z_alpha if torch.is_tensor(z_alpha) else None)
+    B, C, H, W = x_ref.shape
+    assert x_src.shape == x_ref.shape and flo.shape == (B, 2, H, W)
+    lib = _lib.lib()
+    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x_ref.device)
+    with _device_of(x_ref):
+        st = lib.fldr_warp_metric_fwd(_lib.ptr(x_ref), _lib.strides(x_ref), _lib.ptr(x_src), _lib.strides(x_src),
+                                      _lib.ptr(flo), _lib.strides(flo), float(z_alpha), _lib.ptr(out),
+                                      B, C, H, W, 1 if withmask else 0, _stream_ptr(x_ref.device))
+    _lib.check(st)
+    return out

@@ -13,6 +13,8 @@
  *                       (kernel_Correlation_rearrange 17-42 x2 + kernel_Correlation_updateOutput 44-112)
  *   fldr_corr81_bwd  <- OpticalFlow/correlation.py:353-409  _FunctionCorrelation.backward
  *                       (kernel_Correlation_updateGradFirst 114-176, updateGradSecond 178-242)
+ *   fldr_bwarp_fwd, fldr_warp_metric_fwd  <- fLDRnet.py:546-581 DCTVFInet.bwarp and the metric at 442-446
+ *                       (the step just before the image splat)
  *
  * Conventions
  *   - plain C: raw device pointers, explicit element strides, explicit sizes, a CUDA stream handle.
@@ -143,6 +145,30 @@ int fldr_corr81_bwd(const float* first, const int64_t* first_strides,
                     float* grad_first, float* grad_second,
                     int B, int C, int H, int W,
                     void* ws, size_t ws_bytes, fldr_stream_t stream);
+
+/* ------------------------------------------------- backward warp + splat metric (next row) ---- */
+
+/*
+ * DCTVFInet.bwarp(x, flo, withmask) of fLDRnet.py:546-581: out[n,c,y,x] = bilinear sample of x[n,c] at
+ *   ix = ((2*(x+u)/max(W-1,1) - 1 + 1) * W - 1) / 2   (the reference's normalisation + grid_sample's
+ *   align_corners=False default, zero padding), iy likewise, times the mask
+ *   [sum of in-frame bilinear weights >= 0.999] when with_mask != 0 (569-578).
+ *   x [N,C,H,W] with strides (non-negative H/W strides), flow [N,2,H,W] with strides, out [N,C,H,W] contiguous.
+ */
+int fldr_bwarp_fwd(const float* x, const int64_t* x_strides,
+                   const float* flow, const int64_t* flow_strides,
+                   float* out, int N, int C, int H, int W, int with_mask, fldr_stream_t stream);
+
+/*
+ * The splat metric of fLDRnet.py:442-446 in one pass, without materialising the warped image:
+ *   out[n,0,y,x] = (1/C) * sum_c alpha * | ref[n,c,y,x] - bwarp(src, flow)[n,c,y,x] |
+ *   ref, src [N,C,H,W] with strides; out [N,1,H,W] contiguous; alpha = z_alpha[i] rounded to fp32.
+ */
+int fldr_warp_metric_fwd(const float* ref, const int64_t* ref_strides,
+                         const float* src, const int64_t* src_strides,
+                         const float* flow, const int64_t* flow_strides,
+                         float alpha, float* out, int N, int C, int H, int W, int with_mask,
+                         fldr_stream_t stream);
 
 #ifdef __cplusplus
 }

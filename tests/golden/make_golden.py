@@ -69,7 +69,46 @@ def corr_case(name, B, C, H, W, seed):
     print(name, tuple(out.shape))
 
 
+def _reference_bwarp():
+    """The reference's own ``bwarp`` method (fLDRnet.py:546-581), lifted out of its class by ast and run on the CPU.
+    (Importing fLDRnet.py whole needs cupy and a GPU; the method itself is plain torch.)"""
+    import ast
+    import textwrap
+    import types
+    src = open("/root/reference/fLDRnet.py").read()
+    tree = ast.parse(src)
+    fn = next(n for c in tree.body if isinstance(c, ast.ClassDef) and c.name == "DCTVFInet"
+              for n in c.body if isinstance(n, ast.FunctionDef) and n.name == "bwarp")
+    code = textwrap.dedent("\n".join(src.splitlines()[fn.lineno - 1:fn.end_lineno]))
+    ns = {"torch": torch, "nn": torch.nn}
+    exec(compile(code, "fLDRnet.py:bwarp", "exec"), ns)
+    owner = types.SimpleNamespace(device=torch.device("cpu"))
+    return lambda x, flo, withmask=True: ns["bwarp"](owner, x, flo, withmask=withmask)
+
+
+def warp_case(name, N, C, H, W, regime, scale, seed, alpha=-1.894):
+    bwarp = _reference_bwarp()
+    x0 = synth.image(N, C, H, W, seed=seed)
+    x1 = synth.image(N, C, H, W, seed=seed + 1)
+    fl = synth.flow(N, H, W, regime, seed=seed + 2) * scale
+    out = {"ref": x0, "src": x1, "flow": fl, "alpha": torch.tensor(alpha)}
+    with torch.no_grad():
+        out["bwarp_mask"] = bwarp(x1, fl.clone(), True)
+        out["bwarp_nomask"] = bwarp(x1, fl.clone(), False)
+        z_alpha = torch.tensor([alpha, alpha], dtype=torch.float64)          # fLDRnet.py:360: a double Parameter
+        out["metric"] = torch.mean(z_alpha[0] * torch.abs(x0 - out["bwarp_mask"]), dim=1, keepdim=True)   # fLDRnet.py:443
+    assert out["metric"].dtype == torch.float32
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **{k: v.numpy() for k, v in out.items()})
+    print(name, tuple(out["bwarp_mask"].shape), "masked px", int((out["bwarp_mask"].abs().sum(1) == 0).sum()))
+
+
 if __name__ == "__main__":
+    if "--warp-only" in sys.argv:
+        warp_case("warp_smooth", 2, 3, 24, 40, "F1", 40.0, 110)     # image-like, smooth large flow
+        warp_case("warp_scatter", 1, 2, 17, 23, "F2", 1.0, 120)     # C=2 (a flow warped by a flow, fLDRnet.py:474), odd sizes
+        warp_case("warp_border", 2, 3, 20, 32, "FB", 1.0, 130)      # a quarter of the samples leave the frame
+        warp_case("warp_identity", 1, 3, 8, 12, "F0", 1.0, 140)     # zero flow is NOT the identity (W/(W-1) quirk)
+        sys.exit(0)
     splat_case("splat_smooth", 2, 3, 24, 40, "F1", 40.0, 10)    # image-like C=3, smooth large flow
     splat_case("splat_scatter", 1, 5, 17, 23, "F2", 1.0, 20)    # odd sizes, iid flow, C not multiple of 4
     splat_case("splat_converge", 1, 3, 16, 24, "F3", 1.0, 30)   # max contention

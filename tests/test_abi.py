@@ -88,6 +88,14 @@ def test_argument_validation_needs_no_device(lib):
     assert lib.fldr_corr81_fwd(None, s4, p, s4, p, 1, 4, 8, 8, None, 0, None) == -1
     assert lib.fldr_corr81_fwd(p, s4, p, s4, p, 0, 4, 8, 8, None, 0, None) == -1
     assert lib.fldr_corr81_bwd(p, s4, p, s4, None, s4, p, p, 1, 4, 8, 8, None, 0, None) == -1
+    # backward warp / splat metric (next row)
+    assert lib.fldr_bwarp_fwd(None, s4, p, s4, p, 1, 3, 8, 8, 1, None) == -1
+    assert lib.fldr_bwarp_fwd(p, s4, p, s4, p, 1, 0, 8, 8, 1, None) == -1
+    assert lib.fldr_bwarp_fwd(p, s4, p, s4, p, 1, 3, 65536, 65536, 1, None) == -4
+    neg = (ctypes.c_int64 * 4)(64, 64, -8, 1)
+    assert lib.fldr_bwarp_fwd(p, neg, p, s4, p, 1, 3, 8, 8, 1, None) == -4          # flipped views are refused, not mis-read
+    assert lib.fldr_warp_metric_fwd(p, s4, None, s4, p, s4, 1.0, p, 1, 3, 8, 8, 1, None) == -1
+    assert lib.fldr_warp_metric_fwd(p, s4, p, s4, p, s4, 1.0, p, 1, 3, 8, 0, 1, None) == -1
 
 
 def test_host_mirror_names_and_cpu_errors(lib):
@@ -105,6 +113,11 @@ def test_host_mirror_names_and_cpu_errors(lib):
         C.FunctionCorrelation(tensorFirst=x, tensorSecond=x)
     with pytest.raises(AssertionError):
         S.FunctionSoftsplat(x, fl, None, "nearest")
+    import fldr_vfi_b200.warp as Wp
+    with pytest.raises(NotImplementedError):                      # no CPU path for the warp row either
+        Wp.bwarp(x, fl)
+    with pytest.raises(NotImplementedError):
+        Wp.splat_metric(x, x, fl, -1.9)
 
 
 def test_dropin_import_names_shadow_reference_modules(lib):

@@ -24,3 +24,6 @@ def test_fldrnet_psnr_parity_with_dropins():
     assert d["softSplat_module"]["ours"].endswith(os.path.join("dropin", "softSplat.py"))
     assert d["softSplat_module"]["reference"].endswith(os.path.join("_ref", "softSplat.py"))
     assert d["psnr_abs_diff_dB"] <= 0.01, d
+    # with the bwarp method replaced by the fused gather kernel as well
+    assert "fldr_vfi_b200.warp.bwarp" in d["softSplat_module"]["ours_warp"]
+    assert d["with_bwarp_row"]["psnr_abs_diff_dB"] <= 0.01, d

@@ -134,3 +134,49 @@ def test_kat_correlation():
     assert torch.allclose(out2[:, ch, 4:-4, 4:-4], (f * f).mean(1)[:, 4:-4, 4:-4], atol=1e-6)
     # the 4-pixel border ring sees zero padding: displacement (-4,-4) at pixel (0,0) reads outside the frame
     assert float(out[0, 0, 0, 0]) == 0.0
+
+
+# ---------------------------------------------------------------- backward warp + splat metric
+WARP_CASES = ["warp_smooth", "warp_scatter", "warp_border", "warp_identity"]
+
+
+@pytest.mark.parametrize("name", WARP_CASES)
+def test_warp_oracle_vs_golden(name):
+    """The explicit restatement against the outputs of the reference's own bwarp source (tests/golden/make_golden.py)."""
+    from oracle import warp_oracle as wo
+    g = load_golden(name)
+    a = float(g["alpha"])
+    for key, got in (("bwarp_mask", wo.bwarp(g["src"], g["flow"], True)), ("bwarp_nomask", wo.bwarp(g["src"], g["flow"], False)),
+                     ("metric", wo.warp_metric(g["ref"], g["src"], g["flow"], a))):
+        err = float((got - g[key]).abs().max())
+        assert err <= 2e-6, (name, key, err)
+    # the mask decision itself is identical: no pixel kept on one side and zeroed on the other
+    kept_ref = g["bwarp_mask"].abs().sum(1) > 0
+    kept_got = wo.bwarp(g["src"], g["flow"], True).abs().sum(1) > 0
+    assert bool((kept_ref == kept_got).all())
+
+
+def test_warp_kat_zero_flow_is_not_identity_but_integer_grid_is():
+    """Reference quirk (fLDRnet.py:565-568): coordinates are normalised with W-1 and sampled with align_corners=False,
+    so zero flow resamples at X*W/(W-1) - 0.5.  A flow of u = (x + 0.5)*(W-1)/W - x undoes it exactly."""
+    from oracle import warp_oracle as wo
+    H, W = 6, 8
+    x = synth.image(1, 3, H, W, seed=7)
+    zero = wo.bwarp(x, torch.zeros(1, 2, H, W), withmask=False)
+    assert float((zero - x).abs().max()) > 1e-3
+    gx = torch.arange(W, dtype=torch.float64).view(1, 1, 1, W).expand(1, 1, H, W)
+    gy = torch.arange(H, dtype=torch.float64).view(1, 1, H, 1).expand(1, 1, H, W)
+    fl = torch.cat([(gx + 0.5) * (W - 1) / W - gx, (gy + 0.5) * (H - 1) / H - gy], 1).float()
+    ident, msum = wo.bwarp(x, fl, withmask=True, return_mask=True)
+    assert float((ident - x).abs().max()) < 1e-5 and float(msum.min()) > 0.999
+
+
+def test_warp_kat_mask_and_metric():
+    from oracle import warp_oracle as wo
+    H, W = 8, 8
+    x = torch.ones(1, 2, H, W)
+    fl = torch.zeros(1, 2, H, W)
+    fl[:, 0] = 100.0                                              # everything samples outside the frame
+    assert float(wo.bwarp(x, fl).abs().max()) == 0.0
+    z = wo.warp_metric(x, x, fl, -2.0)                            # |1 - 0| * -2, mean over channels
+    assert z.shape == (1, 1, H, W) and float((z + 2.0).abs().max()) == 0.0
