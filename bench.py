@@ -395,6 +395,18 @@ def next_rows_probe(devin, peak):
             ms = med(fn)
             out[name] = {"ms_per_call": round(ms, 4), "algorithmic_bytes": nbytes, "GBps": round(nbytes / ms / 1e6, 1),
                          "frac_of_peak": round(nbytes / ms / 1e6 / peak, 3)}
+    # rank 2: occlusion softmax + six-way blend (fLDRnet.py:510-524), float64 output
+    import fldr_vfi_b200.blend as Bl
+    from oracle import synth   # input generator only
+    logits = (synth.grad((N, 6, H, W), seed=77) * 3.0).to(x0.device)
+    extra = [synth.image(N, C, H, W, seed=78 + k).to(x0.device) for k in range(4)]
+    tv = torch.full((N, 1, 1, 1), 0.5, device=x0.device)
+    T = torch.ones(1, dtype=torch.float64, device=x0.device)
+    with torch.no_grad():
+        ms = med(lambda: Bl.occ_blend(logits, T, tv, *extra, x0, x1))
+    nbytes = px * (6 * 4 + 6 * C * 4 + C * 8)
+    out["occ_blend_C3_f64"] = {"ms_per_call": round(ms, 4), "algorithmic_bytes": nbytes, "GBps": round(nbytes / ms / 1e6, 1),
+                               "frac_of_peak": round(nbytes / ms / 1e6 / peak, 3)}
     return out
 
 

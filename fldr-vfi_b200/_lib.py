@@ -41,6 +41,9 @@ SYMBOLS = {
     "fldr_warp_metric_fwd": (ctypes.c_int, [c_float_p, c_i64_p, c_float_p, c_i64_p, c_float_p, c_i64_p, ctypes.c_float,
                                             c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_void_p]),
+    "fldr_occ_blend_fwd": (ctypes.c_int, [c_float_p, c_i64_p, ctypes.POINTER(ctypes.c_void_p), c_i64_p, c_float_p,
+                                          ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
 }
 
 SPLAT_MODES = {"summation": 0, "average": 1, "linear": 2, "softmax": 3, "raw": 4}

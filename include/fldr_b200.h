@@ -15,6 +15,7 @@
  *                       (kernel_Correlation_updateGradFirst 114-176, updateGradSecond 178-242)
  *   fldr_bwarp_fwd, fldr_warp_metric_fwd  <- fLDRnet.py:546-581 DCTVFInet.bwarp and the metric at 442-446
  *                       (the step just before the image splat)
+ *   fldr_occ_blend_fwd  <- fLDRnet.py:510-524 occlusion softmax + six-way blend (the last step; 8f rank 2)
  *
  * Conventions
  *   - plain C: raw device pointers, explicit element strides, explicit sizes, a CUDA stream handle.
@@ -169,6 +170,23 @@ int fldr_warp_metric_fwd(const float* ref, const int64_t* ref_strides,
                          const float* flow, const int64_t* flow_strides,
                          float alpha, float* out, int N, int C, int H, int W, int with_mask,
                          fldr_stream_t stream);
+
+/* ------------------------------------- occlusion softmax + image synthesis (next row) ---------- */
+
+/*
+ * fLDRnet.py:510-524 in one pass, in float64 like the reference (its temperature is a float64 Parameter):
+ *   occ = softmax(logits[:, 0:6] / T, dim=1);  a_k = (k even ? 1-t : t) * occ_k
+ *   out = (a0*img0 + a1*img1 + a2*img2 + a3*img3 + a4*img4 + a5*img5) / (a0 + ... + a5)
+ *   logits      [N,>=6,H,W] float32 with strides (channels 0..5 are read)
+ *   images      host array of 6 device pointers, each [N,C,H,W] float32: warped_img0, warped_img1, im0_tot, im1_tot,
+ *               x0, x1 (the order of lines 518-521); image_strides = host array of 6 x 4 element strides
+ *   t_value     device, float32, one per sample, t_stride elements apart;  temperature  device, one float64 (T_param)
+ *   out         [N,C,H,W] float64 contiguous;  occ0  [N,1,H,W] float64 contiguous or NULL (occ[:, 0:1], line 512)
+ */
+int fldr_occ_blend_fwd(const float* logits, const int64_t* logits_strides,
+                       const float* const* images, const int64_t* image_strides,
+                       const float* t_value, int64_t t_stride, const double* temperature,
+                       double* out, double* occ0, int N, int C, int H, int W, fldr_stream_t stream);
 
 #ifdef __cplusplus
 }

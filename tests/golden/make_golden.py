@@ -102,7 +102,41 @@ def warp_case(name, N, C, H, W, regime, scale, seed, alpha=-1.894):
     print(name, tuple(out["bwarp_mask"].shape), "masked px", int((out["bwarp_mask"].abs().sum(1) == 0).sum()))
 
 
+def _reference_blend_lines():
+    """fLDRnet.py's own source lines from ``num_softmax_combs = 6`` to ``out_l /=divisor`` (510-524), dedented."""
+    import textwrap
+    lines = open("/root/reference/fLDRnet.py").read().splitlines()
+    i0 = next(i for i, l in enumerate(lines) if "num_softmax_combs = 6" in l)
+    i1 = next(i for i, l in enumerate(lines) if i > i0 and "out_l /=divisor" in l)
+    return textwrap.dedent("\n".join(l for l in lines[i0:i1 + 1] if l.strip()))
+
+
+def blend_case(name, N, C, H, W, seed, temperature=1.0, t=0.5):
+    import types
+    import torch.nn.functional as F
+    code = _reference_blend_lines()
+    imgs = [synth.image(N, C, H, W, seed=seed + k) for k in range(6)]
+    refine_out = synth.grad((N, 8, H, W), seed=seed + 10) * 3.0          # 6 logits + 2 spare channels, like the U-Net output
+    t_value = torch.full((N, 1), t) + 0.1 * torch.arange(N, dtype=torch.float32).view(N, 1) / max(N, 1)
+    x_l = torch.stack([imgs[4], imgs[5]], 2)                             # [N,C,2,H,W] as in the model
+    owner = types.SimpleNamespace(T_param=torch.full((1,), temperature, dtype=torch.float64))     # fLDRnet.py:357
+    ns = {"torch": torch, "F": F, "self": owner, "refine_out": refine_out, "t_value": t_value.view(N, 1, 1, 1),
+          "warped_img0_l": imgs[0], "warped_img1_l": imgs[1], "im0_tot": imgs[2], "im1_tot": imgs[3], "x_l": x_l}
+    with torch.no_grad():
+        exec(compile(code, "fLDRnet.py:510-524", "exec"), ns)
+    assert ns["out_l"].dtype == torch.float64
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), refine_out=refine_out.numpy(), t_value=t_value.numpy(),
+                        temperature=np.float64(temperature), **{f"img{k}": imgs[k].numpy() for k in range(6)},
+                        out=ns["out_l"].numpy(), occ0=ns["occ_0_l"].numpy())
+    print(name, tuple(ns["out_l"].shape), ns["out_l"].dtype)
+
+
 if __name__ == "__main__":
+    if "--blend-only" in sys.argv:
+        blend_case("blend_t05", 2, 3, 16, 24, 210)                       # t = 0.5 / 0.55, T = 1 (the shipped checkpoint)
+        blend_case("blend_temp", 1, 3, 9, 13, 220, temperature=0.37, t=0.25)   # odd sizes, learned temperature, t != 0.5
+        blend_case("blend_c1", 3, 1, 8, 8, 230, temperature=2.0, t=0.8)
+        sys.exit(0)
     if "--warp-only" in sys.argv:
         warp_case("warp_smooth", 2, 3, 24, 40, "F1", 40.0, 110)     # image-like, smooth large flow
         warp_case("warp_scatter", 1, 2, 17, 23, "F2", 1.0, 120)     # C=2 (a flow warped by a flow, fLDRnet.py:474), odd sizes

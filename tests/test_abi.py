@@ -96,6 +96,14 @@ def test_argument_validation_needs_no_device(lib):
     assert lib.fldr_bwarp_fwd(p, neg, p, s4, p, 1, 3, 8, 8, 1, None) == -4          # flipped views are refused, not mis-read
     assert lib.fldr_warp_metric_fwd(p, s4, None, s4, p, s4, 1.0, p, 1, 3, 8, 8, 1, None) == -1
     assert lib.fldr_warp_metric_fwd(p, s4, p, s4, p, s4, 1.0, p, 1, 3, 8, 0, 1, None) == -1
+    # occlusion softmax + blend (next row 2)
+    six = (ctypes.c_void_p * 6)(*([16] * 6))
+    s24 = (ctypes.c_int64 * 24)(*([64, 64, 8, 1] * 6))
+    assert lib.fldr_occ_blend_fwd(p, s4, six, s24, p, 1, p, p, None, 1, 3, 8, 0, None) == -1
+    assert lib.fldr_occ_blend_fwd(p, s4, six, s24, p, 1, None, p, None, 1, 3, 8, 8, None) == -1
+    hole = (ctypes.c_void_p * 6)(16, 16, None, 16, 16, 16)
+    assert lib.fldr_occ_blend_fwd(p, s4, hole, s24, p, 1, p, p, None, 1, 3, 8, 8, None) == -1
+    assert lib.fldr_occ_blend_fwd(p, s4, six, s24, p, 1, p, p, None, 1, 3, 65536, 65536, None) == -4
 
 
 def test_host_mirror_names_and_cpu_errors(lib):
@@ -118,6 +126,9 @@ def test_host_mirror_names_and_cpu_errors(lib):
         Wp.bwarp(x, fl)
     with pytest.raises(NotImplementedError):
         Wp.splat_metric(x, x, fl, -1.9)
+    import fldr_vfi_b200.blend as Bl
+    with pytest.raises(NotImplementedError):
+        Bl.occ_blend(torch.zeros(1, 6, 4, 4), torch.ones(1, dtype=torch.float64), torch.full((1, 1), 0.5), x, x, x, x, x, x)
 
 
 def test_dropin_import_names_shadow_reference_modules(lib):

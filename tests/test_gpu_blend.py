@@ -1,0 +1,84 @@
+"""GPU parity tests for the occlusion softmax + image synthesis row: CUDA path through the C-ABI vs
+the float64 oracle and the golden vectors of fLDRnet.py's own lines 510-524; views, t per sample, the 4K shape against the
+reference's operator sequence run in torch on the same GPU."""
+import pytest
+import torch
+
+from oracle import blend_oracle as bo
+from oracle import synth
+from util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+BLEND_CASES = ["blend_t05", "blend_temp", "blend_c1"]
+TOL = 2e-14      # float64 end to end; only exp() may differ from the host libm by an ulp
+
+
+def _mod(cuda_lib):
+    import fldr_vfi_b200.blend as Bl
+    return Bl
+
+
+@pytest.mark.parametrize("name", BLEND_CASES)
+def test_vs_golden(cuda_lib, name):
+    Bl = _mod(cuda_lib)
+    g = load_golden(name)
+    T = g["temperature"].reshape(1).double().cuda()
+    with torch.no_grad():
+        out, occ0 = Bl.occ_blend(g["refine_out"].cuda(), T, g["t_value"].cuda(), *[g[f"img{k}"].cuda() for k in range(6)],
+                                 return_occ0=True)
+    assert out.dtype == torch.float64 and out.is_contiguous() and occ0.shape == g["occ0"].shape
+    assert float((out.cpu() - g["out"]).abs().max()) <= TOL, name
+    assert float((occ0.cpu() - g["occ0"]).abs().max()) <= TOL, name
+
+
+@pytest.mark.parametrize("N,C,H,W", [(1, 3, 37, 61), (3, 3, 16, 130), (2, 5, 9, 7), (1, 1, 1, 1)])
+def test_vs_oracle_shapes_and_views(cuda_lib, N, C, H, W):
+    Bl = _mod(cuda_lib)
+    imgs = [synth.image(N, C, H, W, seed=400 + k) for k in range(4)]
+    x_l = torch.stack([synth.image(N, C, H, W, seed=410), synth.image(N, C, H, W, seed=411)], 2)     # [N,C,2,H,W]: strided x0, x1
+    refine = synth.grad((N, 9, H, W), seed=420) * 4.0
+    t = torch.rand(N, 1, generator=torch.Generator().manual_seed(5))
+    T = torch.tensor([0.73], dtype=torch.float64)
+    want, occ_w = bo.occ_blend(refine, T, t, *imgs, x_l[:, :, 0], x_l[:, :, 1])
+    xd = x_l.cuda()
+    with torch.no_grad():
+        got, occ_g = Bl.occ_blend(refine.cuda(), T.cuda(), t.cuda().view(N, 1, 1, 1), *[i.cuda() for i in imgs], xd[:, :, 0], xd[:, :, 1],
+                                  return_occ0=True)
+    assert float((got.cpu() - want).abs().max()) <= TOL
+    assert float((occ_g.cpu() - occ_w).abs().max()) <= TOL
+
+
+def test_errors(cuda_lib):
+    Bl = _mod(cuda_lib)
+    x = torch.zeros(1, 3, 8, 8, device="cuda")
+    lg = torch.zeros(1, 6, 8, 8, device="cuda")
+    t = torch.full((1, 1), 0.5, device="cuda")
+    with pytest.raises(TypeError):                      # a float32 temperature would silently change the arithmetic type
+        Bl.occ_blend(lg, torch.ones(1, device="cuda"), t, x, x, x, x, x, x)
+    with pytest.raises(NotImplementedError):
+        Bl.occ_blend(lg.requires_grad_(True), torch.ones(1, dtype=torch.float64, device="cuda"), t, x, x, x, x, x, x)
+
+
+def test_4k_vs_reference_operator_sequence(cuda_lib):
+    Bl = _mod(cuda_lib)
+    H, W = 2304, 4096
+    imgs = [synth.image(1, 3, H, W, seed=500 + k).cuda() for k in range(6)]
+    refine = (synth.grad((1, 6, H, W), seed=510) * 3.0).cuda()
+    t_value = torch.full((1, 1, 1, 1), 0.5, device="cuda")
+    T = torch.ones(1, dtype=torch.float64, device="cuda")
+    with torch.no_grad():
+        got = Bl.occ_blend(refine, T, t_value, *imgs)
+        occ_all = torch.nn.functional.softmax(refine[:, 0:6] / T, dim=1)               # fLDRnet.py:511-524 restated in torch
+        tv = t_value
+        divisor = ((1 - tv) * occ_all[:, 0, :].unsqueeze(1) + tv * occ_all[:, 1, :].unsqueeze(1)
+                   + (1 - tv) * occ_all[:, 2, :].unsqueeze(1) + tv * occ_all[:, 3, :].unsqueeze(1))
+        out = (1 - tv) * occ_all[:, 0, :].unsqueeze(1) * imgs[0] + tv * occ_all[:, 1, :].unsqueeze(1) * imgs[1]
+        out += (1 - tv) * occ_all[:, 2, :].unsqueeze(1) * imgs[2] + tv * occ_all[:, 3, :].unsqueeze(1) * imgs[3]
+        out += (1 - tv) * occ_all[:, 4, :].unsqueeze(1) * imgs[4] + tv * occ_all[:, 5, :].unsqueeze(1) * imgs[5]
+        divisor += (1 - tv) * occ_all[:, 4, :].unsqueeze(1) + tv * occ_all[:, 5, :].unsqueeze(1)
+        out /= divisor
+    assert out.dtype == torch.float64
+    assert float((got - out).abs().max()) <= 1e-13
+    # convexity: the blend of images in [-1, 1] stays in [-1, 1]
+    assert float(got.abs().max()) <= 1.0 + 1e-12

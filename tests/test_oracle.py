@@ -180,3 +180,34 @@ def test_warp_kat_mask_and_metric():
     assert float(wo.bwarp(x, fl).abs().max()) == 0.0
     z = wo.warp_metric(x, x, fl, -2.0)                            # |1 - 0| * -2, mean over channels
     assert z.shape == (1, 1, H, W) and float((z + 2.0).abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------- occlusion softmax + image synthesis
+BLEND_CASES = ["blend_t05", "blend_temp", "blend_c1"]
+
+
+@pytest.mark.parametrize("name", BLEND_CASES)
+def test_blend_oracle_vs_golden(name):
+    """The restatement against the outputs of fLDRnet.py's own lines 510-524 (tests/golden/make_golden.py)."""
+    from oracle import blend_oracle as bo
+    g = load_golden(name)
+    T = g["temperature"].reshape(1).double()
+    out, occ0 = bo.occ_blend(g["refine_out"], T, g["t_value"], *[g[f"img{k}"] for k in range(6)])
+    assert out.dtype == torch.float64 and g["out"].dtype == torch.float64
+    assert float((out - g["out"]).abs().max()) <= 1e-15 and float((occ0 - g["occ0"]).abs().max()) <= 1e-15
+
+
+def test_blend_kat():
+    """Equal logits and t = 0.5: every weight is 1/12, so the result is the plain mean of the six images; one dominant
+    logit selects its image whatever t is (the divisor normalises t away)."""
+    from oracle import blend_oracle as bo
+    N, C, H, W = 1, 3, 4, 5
+    imgs = [synth.image(N, C, H, W, seed=300 + k) for k in range(6)]
+    T = torch.ones(1, dtype=torch.float64)
+    out, occ0 = bo.occ_blend(torch.zeros(N, 6, H, W), T, torch.full((N, 1), 0.5), *imgs)
+    assert float((out - sum(i.double() for i in imgs) / 6).abs().max()) < 1e-15
+    assert float((occ0 - 1 / 6).abs().max()) < 1e-15
+    logits = torch.zeros(N, 6, H, W)
+    logits[:, 3] = 800.0
+    out, _ = bo.occ_blend(logits, T, torch.full((N, 1), 0.3), *imgs)
+    assert float((out - imgs[3].double()).abs().max()) < 1e-12
