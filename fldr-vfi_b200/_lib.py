@@ -32,6 +32,8 @@ SYMBOLS = {
     "fldr_corr81_fwd": (ctypes.c_int, [c_float_p, c_i64_p, c_float_p, c_i64_p, c_float_p,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "fldr_corr81_fwd_act": (ctypes.c_int, [c_float_p, c_i64_p, c_float_p, c_i64_p, c_float_p, ctypes.c_int64, ctypes.c_float,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "fldr_corr81_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 4),
     "fldr_corr81_bwd": (ctypes.c_int, [c_float_p, c_i64_p, c_float_p, c_i64_p, c_float_p, c_i64_p,
                                        c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

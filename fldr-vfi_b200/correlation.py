@@ -75,3 +75,35 @@ class ModuleCorrelation(torch.nn.Module):
 
     def forward(self, tensorFirst, tensorSecond):
         return FunctionCorrelation(tensorFirst, tensorSecond)
+
+
+def FunctionCorrelationLeakyReLU(tensorFirst, tensorSecond, negative_slope=0.1, out=None):
+    """Next row: ``leaky_relu(FunctionCorrelation(first, second), negative_slope)`` as PWC-Net's
+    decoder computes it (PWCNet.py:146-158), with the activation fused into the correlation's store epilogue.
+
+    ``out``: optional preallocated contiguous buffer ``[B, Ctot >= 81, H, W]`` - the volume is written into
+    ``out[:, :81]`` (the first block of ``torch.cat([tensorVolume, tensorFirst, tensorFlow, tensorFeat], 1)``,
+    PWCNet.py:160) and that view is returned, so no separate concatenation copy of the volume is needed.
+    Forward only: inputs that require grad while grad mode is on raise (use FunctionCorrelation + F.leaky_relu)."""
+    if not tensorFirst.is_cuda:
+        raise NotImplementedError()
+    _check_cuda_f32("first", tensorFirst)
+    _check_cuda_f32("second", tensorSecond)
+    if torch.is_grad_enabled() and (tensorFirst.requires_grad or tensorSecond.requires_grad):
+        raise NotImplementedError("FunctionCorrelationLeakyReLU is forward-only: call under torch.no_grad()")
+    assert (tensorFirst.is_contiguous() == True)
+    assert (tensorSecond.is_contiguous() == True)
+    assert tensorFirst.shape == tensorSecond.shape
+    B, C, H, W = tensorFirst.shape
+    if out is None:
+        out = torch.empty((B, 81, H, W), dtype=torch.float32, device=tensorFirst.device)
+    else:
+        _check_cuda_f32("out", out)
+        assert out.is_contiguous() and out.shape[0] == B and out.shape[1] >= 81 and out.shape[2:] == (H, W)
+    lib = _lib.lib()
+    with _device_of(tensorFirst):
+        st = lib.fldr_corr81_fwd_act(_lib.ptr(tensorFirst), _lib.strides(tensorFirst), _lib.ptr(tensorSecond),
+                                     _lib.strides(tensorSecond), _lib.ptr(out), out.stride(0), float(negative_slope),
+                                     B, C, H, W, _stream_ptr(tensorFirst.device))
+    _lib.check(st)
+    return out[:, :81]

@@ -18,6 +18,15 @@ namespace fldr {
 constexpr int kPad = 4;
 constexpr int kD = 9;
 
+// Forward epilogue: mean over channels, then the activation PWC-Net applies to every cost volume
+// (leaky_relu(., 0.1), PWCNet.py:146-158; slope 1 = none), stored with an arbitrary sample stride so the volume can
+// land directly in the first 81 channels of the decoder's concatenation buffer (PWCNet.py:160).
+struct FwdEpilogue {
+    float slope;            // negative_slope, 1 = identity
+    long long out_sn;       // elements between consecutive samples of the output
+};
+__device__ __forceinline__ float corr_act(float v, float slope) { return v > 0.f ? v : v * slope; }
+
 // ------------------------------------------------------------------------------------------------
 // Forward.  CTA = 32 x 8 output pixels, 192 threads: thread = (4-pixel group, row, dy-group of 3).
 // Per channel and thread: 1 LDS.128 (first) + 9 LDS.128 (second, 3 rows x 12 floats) feed 108 FFMA.
@@ -28,7 +37,7 @@ constexpr int F2W = TW + 2 * kPad, F2H = TH + 2 * kPad;
 }  // namespace fwd
 
 __global__ void __launch_bounds__(fwd::NT) corr81_fwd_kernel(View4 f1, View4 f2, float* __restrict__ out, int C, int H,
-                                                             int W) {
+                                                             int W, FwdEpilogue ep) {
     using namespace fwd;
     __shared__ __align__(16) float s1[CK][TH][TW];
     __shared__ __align__(16) float s2[CK][F2H][F2W];
@@ -85,8 +94,8 @@ __global__ void __launch_bounds__(fwd::NT) corr81_fwd_kernel(View4 f1, View4 f2,
     if (y >= H || x >= W) return;
     const float rc = 1.0f / (float)C;   // sum * (1/C): within 1 ulp of the reference's sum / C (exact for power-of-two C)
     const long long HW = (long long)H * W;
-    float* ob = out + (long long)b * 81 * HW + (long long)y * W + x;
-    const bool vec = ((W & 3) == 0) && (x + 3 < W);
+    float* ob = out + (long long)b * ep.out_sn + (long long)y * W + x;
+    const bool vec = ((W & 3) == 0) && (x + 3 < W) && ((ep.out_sn & 3) == 0);
 #pragma unroll
     for (int d = 0; d < 3; ++d)
 #pragma unroll
@@ -94,11 +103,12 @@ __global__ void __launch_bounds__(fwd::NT) corr81_fwd_kernel(View4 f1, View4 f2,
             float* op = ob + (long long)((dyg * 3 + d) * kD + o) * HW;
             if (vec) {
                 *reinterpret_cast<float4*>(op) =
-                    make_float4(acc[d][o][0] * rc, acc[d][o][1] * rc, acc[d][o][2] * rc, acc[d][o][3] * rc);
+                    make_float4(corr_act(acc[d][o][0] * rc, ep.slope), corr_act(acc[d][o][1] * rc, ep.slope),
+                                corr_act(acc[d][o][2] * rc, ep.slope), corr_act(acc[d][o][3] * rc, ep.slope));
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (x + j < W) op[j] = acc[d][o][j] * rc;
+                    if (x + j < W) op[j] = corr_act(acc[d][o][j] * rc, ep.slope);
             }
         }
 }
@@ -125,11 +135,13 @@ template <int TH> struct Cfg {
 // SPLIT: the channel range of a tile is divided over `ksplit` work items (small pyramid levels have fewer tiles than
 // the GPU has SMs: 20 tiles x 25 chunks at C = 196); partial sums are reduced into the zero-filled output with
 // red.global.add.v4.f32.
-template <int TH, bool SPLIT>
+// ACT: leaky-relu in the epilogue (never together with SPLIT).  STRIDED: output samples ep.out_sn apart instead of
+// 81*H*W (a separate instantiation: the extra 64-bit value costs the dense path its last free registers)
+template <int TH, bool SPLIT, bool ACT, bool STRIDED>
 __global__ void __launch_bounds__(fwdtma::Cfg<TH>::NT, TH == 8 ? 2 : 1)
 corr81_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
                       float* __restrict__ out, int B, int C, int H, int W, int tilesX, int tilesY, int ksplit,
-                      int chunks_per_split) {
+                      int chunks_per_split, const __grid_constant__ FwdEpilogue ep) {
     using namespace fwdtma;
     using K = Cfg<TH>;
     constexpr int STAGES = K::STAGES;
@@ -247,13 +259,17 @@ corr81_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_cons
         const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, b = tile / (tilesX * tilesY);
         const int y = ty * TH + row, x = tx * TW + pg * 4;
         if (y < H && x < W) {      // W % 4 == 0 on this path: the 4-pixel group is all in or all out
-            float* ob = out + (long long)b * 81 * HW + (long long)y * W + x;
+            float* ob = out + (long long)b * (STRIDED ? ep.out_sn : 81 * HW) + (long long)y * W + x;
 #pragma unroll
             for (int d = 0; d < 3; ++d)
 #pragma unroll
                 for (int o = 0; o < kD; ++o) {
                     float* op = ob + (long long)((dyg * 3 + d) * kD + o) * HW;
+                    // SPLIT: partial sums are reduced in memory; the activation runs afterwards (corr81_act_kernel)
                     if (SPLIT) red_add_v4(op, acc[d][o][0] * rc, acc[d][o][1] * rc, acc[d][o][2] * rc, acc[d][o][3] * rc);
+                    else if (ACT) __stcs(reinterpret_cast<float4*>(op),
+                                make_float4(corr_act(acc[d][o][0] * rc, ep.slope), corr_act(acc[d][o][1] * rc, ep.slope),
+                                            corr_act(acc[d][o][2] * rc, ep.slope), corr_act(acc[d][o][3] * rc, ep.slope)));
                     else __stcs(reinterpret_cast<float4*>(op),
                                 make_float4(acc[d][o][0] * rc, acc[d][o][1] * rc, acc[d][o][2] * rc, acc[d][o][3] * rc));
                 }
@@ -261,9 +277,18 @@ corr81_fwd_tma_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_cons
     }
 }
 
+// in-place activation of a channel-split result (small pyramid levels only: a few hundred KB)
+__global__ void __launch_bounds__(256) corr81_act_kernel(float* __restrict__ out, long long per_sample, long long out_sn,
+                                                         float slope) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= per_sample) return;
+    float* p = out + blockIdx.y * out_sn + i;
+    *p = corr_act(*p, slope);
+}
+
 template <int TH>
 static int launch_fwd_tma(const View4& f1, const View4& f2, float* out, int B, int C, int H, int W, cudaStream_t s,
-                          bool* used) {
+                          bool* used, const FwdEpilogue& ep) {
     using namespace fwdtma;
     using K = Cfg<TH>;
     *used = false;
@@ -290,17 +315,29 @@ static int launch_fwd_tma(const View4& f1, const View4& f2, float* out, int B, i
     ksplit = (nchunks + cps - 1) / cps;
     const int nitems = ntiles * ksplit;
     const int grid = nitems < slots ? nitems : slots;
+    const bool strided = ep.out_sn != (long long)81 * H * W;
     cudaError_t e;
     if (ksplit > 1) {
-        e = cudaMemsetAsync(out, 0, (size_t)B * 81 * H * W * sizeof(float), s);
+        const size_t per_sample = (size_t)81 * H * W;
+        e = (size_t)ep.out_sn == per_sample
+                ? cudaMemsetAsync(out, 0, (size_t)B * per_sample * sizeof(float), s)
+                : cudaMemset2DAsync(out, (size_t)ep.out_sn * sizeof(float), 0, per_sample * sizeof(float), (size_t)B, s);
         if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
-        e = cudaFuncSetAttribute(corr81_fwd_tma_kernel<TH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
+        auto kern = strided ? corr81_fwd_tma_kernel<TH, true, false, true> : corr81_fwd_tma_kernel<TH, true, false, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
         if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
-        corr81_fwd_tma_kernel<TH, true><<<grid, K::NT, K::SMEM_BYTES, s>>>(tm1, tm2, out, B, C, H, W, tilesX, tilesY, ksplit, cps);
+        kern<<<grid, K::NT, K::SMEM_BYTES, s>>>(tm1, tm2, out, B, C, H, W, tilesX, tilesY, ksplit, cps, ep);
+        if (ep.slope != 1.0f) {
+            dim3 ag((unsigned)((per_sample + 255) / 256), (unsigned)B);
+            corr81_act_kernel<<<ag, 256, 0, s>>>(out, (long long)per_sample, ep.out_sn, ep.slope);
+        }
     } else {
-        e = cudaFuncSetAttribute(corr81_fwd_tma_kernel<TH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
+        const bool act = ep.slope != 1.0f;
+        auto kern = act ? (strided ? corr81_fwd_tma_kernel<TH, false, true, true> : corr81_fwd_tma_kernel<TH, false, true, false>)
+                        : (strided ? corr81_fwd_tma_kernel<TH, false, false, true> : corr81_fwd_tma_kernel<TH, false, false, false>);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
         if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
-        corr81_fwd_tma_kernel<TH, false><<<grid, K::NT, K::SMEM_BYTES, s>>>(tm1, tm2, out, B, C, H, W, tilesX, tilesY, 1, nchunks);
+        kern<<<grid, K::NT, K::SMEM_BYTES, s>>>(tm1, tm2, out, B, C, H, W, tilesX, tilesY, 1, nchunks, ep);
     }
     *used = true;
     return check_launch();
@@ -460,13 +497,13 @@ extern "C" size_t fldr_corr81_fwd_workspace_bytes(int B, int C, int H, int W) {
     return 0;
 }
 
-extern "C" int fldr_corr81_fwd(const float* first, const int64_t* first_strides, const float* second,
-                               const int64_t* second_strides, float* out, int B, int C, int H, int W, void* ws,
-                               size_t ws_bytes, fldr_stream_t stream) {
-    (void)ws; (void)ws_bytes;
+static int corr81_fwd_impl(const float* first, const int64_t* first_strides, const float* second,
+                           const int64_t* second_strides, float* out, int B, int C, int H, int W, const FwdEpilogue& ep,
+                           fldr_stream_t stream) {
     int st = check_corr_args(B, C, H, W);
     if (st != FLDR_OK) return st;
     if (!first || !second || !first_strides || !second_strides || !out) return FLDR_ERR_INVALID_ARGUMENT;
+    if (ep.out_sn < (long long)81 * H * W || !(ep.slope == ep.slope)) return FLDR_ERR_INVALID_ARGUMENT;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const View4 v1 = make_view(first, first_strides), v2 = make_view(second, second_strides);
     // TMA path: unit inner stride, rows 16-byte aligned, strides positive (views with stride 0 / negative fall back)
@@ -480,12 +517,30 @@ extern "C" int fldr_corr81_fwd(const float* first, const int64_t* first_strides,
         // than one 16-row CTA (180 vs 187 us on the C = 32 level), so 8 is the default
         const bool use16 = th_opt == 16;
         (void)tiles16;
-        st = use16 ? launch_fwd_tma<16>(v1, v2, out, B, C, H, W, s, &used) : launch_fwd_tma<8>(v1, v2, out, B, C, H, W, s, &used);
-        if (st != FLDR_OK || used) return st;
+        // float4 stores / reductions need 16-byte aligned samples
+        if ((ep.out_sn & 3) == 0) {
+            st = use16 ? launch_fwd_tma<16>(v1, v2, out, B, C, H, W, s, &used, ep) : launch_fwd_tma<8>(v1, v2, out, B, C, H, W, s, &used, ep);
+            if (st != FLDR_OK || used) return st;
+        }
     }
     dim3 grid((W + fwd::TW - 1) / fwd::TW, (H + fwd::TH - 1) / fwd::TH, B);
-    corr81_fwd_kernel<<<grid, fwd::NT, 0, s>>>(v1, v2, out, C, H, W);
+    corr81_fwd_kernel<<<grid, fwd::NT, 0, s>>>(v1, v2, out, C, H, W, ep);
     return check_launch();
+}
+
+extern "C" int fldr_corr81_fwd(const float* first, const int64_t* first_strides, const float* second,
+                               const int64_t* second_strides, float* out, int B, int C, int H, int W, void* ws,
+                               size_t ws_bytes, fldr_stream_t stream) {
+    (void)ws; (void)ws_bytes;
+    const FwdEpilogue ep = {1.0f, (long long)81 * H * W};
+    return corr81_fwd_impl(first, first_strides, second, second_strides, out, B, C, H, W, ep, stream);
+}
+
+extern "C" int fldr_corr81_fwd_act(const float* first, const int64_t* first_strides, const float* second,
+                                   const int64_t* second_strides, float* out, int64_t out_sample_stride,
+                                   float negative_slope, int B, int C, int H, int W, fldr_stream_t stream) {
+    const FwdEpilogue ep = {negative_slope, out_sample_stride > 0 ? (long long)out_sample_stride : (long long)81 * H * W};
+    return corr81_fwd_impl(first, first_strides, second, second_strides, out, B, C, H, W, ep, stream);
 }
 
 extern "C" size_t fldr_corr81_bwd_workspace_bytes(int B, int C, int H, int W) {

@@ -137,6 +137,17 @@ int fldr_corr81_fwd(const float* first, const int64_t* first_strides,
                     float* out, int B, int C, int H, int W,
                     void* ws, size_t ws_bytes, fldr_stream_t stream);
 
+/*
+ * Next row (PWCNet.py:146-160): the same cost volume with PWC-Net's leaky_relu(., negative_slope)
+ * applied in the store epilogue (negative_slope = 1 disables it) and written with `out_sample_stride` elements
+ * between samples (>= 81*H*W; 0 means dense), so it can land directly in channels 0..80 of the decoder's
+ * concatenation buffer [B, 81 + ..., H, W] (PWCNet.py:160) - no separate activation pass, no copy by torch.cat.
+ */
+int fldr_corr81_fwd_act(const float* first, const int64_t* first_strides,
+                        const float* second, const int64_t* second_strides,
+                        float* out, int64_t out_sample_stride, float negative_slope,
+                        int B, int C, int H, int W, fldr_stream_t stream);
+
 size_t fldr_corr81_bwd_workspace_bytes(int B, int C, int H, int W);
 
 /* grad_first / grad_second [B,C,H,W] contiguous, either may be NULL (correlation.py:358-361). */

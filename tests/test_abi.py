@@ -88,6 +88,9 @@ def test_argument_validation_needs_no_device(lib):
     assert lib.fldr_corr81_fwd(None, s4, p, s4, p, 1, 4, 8, 8, None, 0, None) == -1
     assert lib.fldr_corr81_fwd(p, s4, p, s4, p, 0, 4, 8, 8, None, 0, None) == -1
     assert lib.fldr_corr81_bwd(p, s4, p, s4, None, s4, p, p, 1, 4, 8, 8, None, 0, None) == -1
+    assert lib.fldr_corr81_fwd_act(p, s4, p, s4, p, 10, 0.1, 1, 4, 8, 8, None) == -1      # sample stride < 81*H*W
+    assert lib.fldr_corr81_fwd_act(p, s4, p, s4, p, 0, float("nan"), 1, 4, 8, 8, None) == -1
+    assert lib.fldr_corr81_fwd_act(p, s4, None, s4, p, 0, 0.1, 1, 4, 8, 8, None) == -1
     # backward warp / splat metric (next row)
     assert lib.fldr_bwarp_fwd(None, s4, p, s4, p, 1, 3, 8, 8, 1, None) == -1
     assert lib.fldr_bwarp_fwd(p, s4, p, s4, p, 1, 0, 8, 8, 1, None) == -1

@@ -93,3 +93,36 @@ def test_native_4k_level_properties_and_crop(cuda_lib):
         yb, xb = slice(max(0, dy), H - max(0, -dy)), slice(max(0, dx), W - max(0, -dx))
         assert float((a[:, ch, ya, xa] - bsw[:, chm, yb, xb]).abs().max()) <= 2e-6
     assert_corr_close(a, co.correlation_fwd(f1, f2), co.correlation_fwd(f1.abs(), f2.abs()), "native level 2 vs oracle")
+
+
+# ---------------------------------------------------------------- next row: fused leaky-relu + concat placement
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 24, 40), (1, 40, 9, 11), (2, 196, 5, 8), (2, 64, 72, 128), (1, 16, 17, 24)])
+def test_leaky_relu_epilogue_and_concat_buffer(cuda_lib, B, C, H, W):
+    """leaky_relu(corr, 0.1) (PWCNet.py:146-158) from the fused epilogue equals the activation applied to the oracle's
+    volume, dense and when written straight into channels 0..80 of a wider concatenation buffer (PWCNet.py:160)."""
+    Cm = _mod(cuda_lib)
+    f1 = synth.features(B, C, H, W, seed=11)
+    f2 = synth.features(B, C, H, W, seed=12)
+    want = torch.nn.functional.leaky_relu(co.correlation_fwd(f1, f2), 0.1)
+    scale = co.correlation_fwd(f1.abs(), f2.abs())
+    with torch.no_grad():
+        got = Cm.FunctionCorrelationLeakyReLU(tensorFirst=f1.cuda(), tensorSecond=f2.cuda())
+        assert_corr_close(got, want, scale, "fused leaky dense")
+        plain = Cm.FunctionCorrelation(tensorFirst=f1.cuda(), tensorSecond=f2.cuda())
+        # (not bit for bit: small levels split the channel range over CTAs and reduce with unordered REDs)
+        assert_corr_close(got, torch.nn.functional.leaky_relu(plain, 0.1).cpu(), scale, "fused vs activation of the plain result")
+        for extra in (C + 2, 7):                                    # 7: sample stride not a multiple of 4 -> generic kernel
+            buf = torch.full((B, 81 + extra, H, W), 123.0, device="cuda")
+            view = Cm.FunctionCorrelationLeakyReLU(tensorFirst=f1.cuda(), tensorSecond=f2.cuda(), out=buf)
+            assert view.data_ptr() == buf.data_ptr() and view.shape == (B, 81, H, W)
+            assert_corr_close(buf[:, :81], want, scale, "fused leaky into concat buffer")
+            assert bool((buf[:, 81:] == 123.0).all()), "channels beyond the volume must be left alone"
+        same = Cm.FunctionCorrelationLeakyReLU(tensorFirst=f1.cuda(), tensorSecond=f2.cuda(), negative_slope=1.0)
+        assert_corr_close(same, plain.cpu(), scale, "slope 1 = plain correlation")
+
+
+def test_leaky_relu_entry_point_is_forward_only(cuda_lib):
+    Cm = _mod(cuda_lib)
+    f = torch.zeros(1, 8, 8, 8, device="cuda", requires_grad=True)
+    with pytest.raises(NotImplementedError):
+        Cm.FunctionCorrelationLeakyReLU(tensorFirst=f, tensorSecond=f)
