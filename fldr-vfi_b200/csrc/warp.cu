@@ -5,8 +5,9 @@
 // kernel, and the metric  z = mean_c(z_alpha * |I_ref - bwarp(I_src, flow)|)  (fLDRnet.py:442-446) by the same kernel
 // with a fused epilogue, so the warped image never reaches memory.
 //
-// Coordinates follow the reference operation by operation, unfused (the __f*_rn intrinsics keep nvcc from contracting
-// them), so the sample positions - and with them the 0.999 mask decision - are bit-identical to the torch path:
+// Coordinates follow the reference operation by operation (the __f*_rn intrinsics keep nvcc from contracting what torch
+// evaluates as separate kernels, and fuse exactly what grid_sample fuses), so the sample positions - and with them the
+// 0.999 mask decision - are bit-identical to the torch path:
 //   X = x + u;  g = 2*X / max(W-1, 1) - 1            (fLDRnet.py:562-566)
 //   ix = ((g + 1) * W - 1) / 2                        (grid_sample, align_corners=False default, :568)
 // i.e. ix = X*W/(W-1) - 0.5: the reference normalises for align_corners=True and samples with False; preserved.
@@ -23,16 +24,35 @@ struct WarpTaps {
     bool keep;           // mask decision (true when masking is off)
 };
 
-__device__ __forceinline__ float warp_source_index(float coord, int size) {
-    const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, coord), (float)max(size - 1, 1)), 1.0f);
-    return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), (float)size), 1.0f), 0.5f);
+// convention 0 - fLDRnet.bwarp (fLDRnet.py:562-568):   g = 2*(i + d) / max(size-1, 1) - 1
+// convention 1 - PWCNet Backward (PWCNet.py:117-137):   g = linspace(-1, 1, size)[i] + d / ((size-1)/2)
+//   torch.linspace on the CPU (where the reference builds its grid, :130) is  fma(step, i, -1)  for the first half and
+//   fma(-step, size-1-i, 1)  for the second, step = 2/(size-1) in float32 - reproduced bit for bit (checked for sizes
+//   17..4096 in tests/test_oracle.py)
+// both: ix = ((g + 1) * size - 1) / 2   (grid_sample's align_corners=False default), rounded once
+__device__ __forceinline__ float warp_source_index(int i, float d, int size, int convention) {
+    float g;
+    if (convention == 0) {
+        g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)i, d)), (float)max(size - 1, 1)), 1.0f);
+    } else {
+        float lin = -1.0f;
+        if (size > 1) {
+            const float step = __fdiv_rn(2.0f, (float)(size - 1));
+            lin = i < size / 2 ? __fmaf_rn(step, (float)i, -1.0f) : __fmaf_rn(-step, (float)(size - 1 - i), 1.0f);
+        }
+        g = __fadd_rn(lin, __fdiv_rn(d, __fmul_rn((float)size - 1.0f, 0.5f)));
+    }
+    // ((g + 1) * size - 1) / 2 with ONE rounding, as torch's grid_sample evaluates it on the CPU vector path and on
+    // CUDA (size/2 and 0.5 are exact, so this fma is that expression rounded once)
+    return __fmaf_rn(__fadd_rn(g, 1.0f), (float)size * 0.5f, -0.5f);
 }
 
 // sh, sw: row / pixel stride of the source plane in elements (32-bit: check_warp_args bounds the plane span)
-__device__ __forceinline__ WarpTaps warp_taps(float u, float v, int x, int y, int H, int W, int sh, int sw, bool with_mask) {
+__device__ __forceinline__ WarpTaps warp_taps(float u, float v, int x, int y, int H, int W, int sh, int sw, bool with_mask,
+                                              int convention) {
     WarpTaps t;
-    const float ix = warp_source_index(__fadd_rn((float)x, u), W);
-    const float iy = warp_source_index(__fadd_rn((float)y, v), H);
+    const float ix = warp_source_index(x, u, W, convention);
+    const float iy = warp_source_index(y, v, H, convention);
     const float fx0 = floorf(ix), fy0 = floorf(iy);
     const float fx1 = fx0 + 1.0f, fy1 = fy0 + 1.0f;
     // compare as floats: NaN / huge coordinates fail every test and sample nothing (torch does the same)
@@ -53,7 +73,8 @@ __device__ __forceinline__ WarpTaps warp_taps(float u, float v, int x, int y, in
         t.w[k] = ok[k] ? w[k] : 0.f;
         msum = __fadd_rn(msum, t.w[k]);          // + 0 for skipped taps: same value as skipping them
     }
-    t.keep = !with_mask || msum >= 0.999f;
+    // fLDRnet: mask < 0.999 -> 0 (fLDRnet.py:573);  PWC-Net: mask > 0.999 -> 1, the rest 0 (PWCNet.py:139-141)
+    t.keep = !with_mask || (convention == 0 ? msum >= 0.999f : msum > 0.999f);
     return t;
 }
 
@@ -65,7 +86,8 @@ __device__ __forceinline__ WarpTaps warp_taps(float u, float v, int x, int y, in
 // METRIC: out is [N,1,H,W] = mean_c(alpha * |ref - warp|), else out is [N,C,H,W] = warp.
 template <bool METRIC, int CU, bool EXACT>
 __global__ void __launch_bounds__(128) bwarp_kernel(View4 src, View4 ref, View4 flow, float* __restrict__ out, int C_,
-                                                    int H, int W, float alpha, int with_mask, int y_base) {
+                                                    int H, int W, float alpha, int with_mask, int y_base,
+                                                    int convention) {
     const int C = EXACT ? CU : C_;
     const int x = (blockIdx.x * 128 + threadIdx.x) * 2, y = y_base + blockIdx.y, n = blockIdx.z;
     if (x >= W) return;
@@ -75,8 +97,8 @@ __global__ void __launch_bounds__(128) bwarp_kernel(View4 src, View4 ref, View4 
     const float* fq = two ? fp + flow.sw : fp;                 // odd-width tail: re-read pixel 0, result unused
     const float u0 = __ldcs(fp), v0 = __ldcs(fp + flow.sc), u1 = __ldcs(fq), v1 = __ldcs(fq + flow.sc);
     WarpTaps t[2];
-    t[0] = warp_taps(u0, v0, x, y, H, W, (int)src.sh, (int)src.sw, with_mask != 0);
-    t[1] = warp_taps(u1, v1, two ? x + 1 : x, y, H, W, (int)src.sh, (int)src.sw, with_mask != 0);
+    t[0] = warp_taps(u0, v0, x, y, H, W, (int)src.sh, (int)src.sw, with_mask != 0, convention);
+    t[1] = warp_taps(u1, v1, two ? x + 1 : x, y, H, W, (int)src.sh, (int)src.sw, with_mask != 0, convention);
     const float* sp = src.p + n * src.sn;
     const float* rp = METRIC ? ref.p + n * ref.sn + y * ref.sh + x * ref.sw : nullptr;
     const int rstep = (METRIC && two) ? (int)ref.sw : 0;
@@ -126,12 +148,12 @@ __global__ void __launch_bounds__(128) bwarp_kernel(View4 src, View4 ref, View4 
 
 template <bool METRIC>
 static int launch_bwarp(const View4& src, const View4& ref, const View4& flow, float* out, int N, int C, int H, int W,
-                        float alpha, int with_mask, cudaStream_t s) {
+                        float alpha, int with_mask, int convention, cudaStream_t s) {
     const int W2 = (W + 1) / 2;
     for (int y0 = 0; y0 < H; y0 += 65535) {          // gridDim.y limit; one launch for every frame under 65 536 rows
         const int rows = H - y0 < 65535 ? H - y0 : 65535;
         dim3 grid((unsigned)((W2 + 127) / 128), (unsigned)rows, (unsigned)N);
-#define FLDR_BWARP(CU, EXACT) bwarp_kernel<METRIC, CU, EXACT><<<grid, 128, 0, s>>>(src, ref, flow, out, C, H, W, alpha, with_mask, y0)
+#define FLDR_BWARP(CU, EXACT) bwarp_kernel<METRIC, CU, EXACT><<<grid, 128, 0, s>>>(src, ref, flow, out, C, H, W, alpha, with_mask, y0, convention)
         if (C == 1) FLDR_BWARP(1, true);
         else if (C == 2) FLDR_BWARP(2, true);
         else if (C == 3) FLDR_BWARP(3, true);
@@ -158,12 +180,14 @@ static int check_warp_args(int N, int C, int H, int W, const View4& src) {
 using namespace fldr;
 
 extern "C" int fldr_bwarp_fwd(const float* x, const int64_t* x_strides, const float* flow, const int64_t* flow_strides,
-                              float* out, int N, int C, int H, int W, int with_mask, fldr_stream_t stream) {
+                              float* out, int N, int C, int H, int W, int with_mask, int convention,
+                              fldr_stream_t stream) {
     if (!x || !x_strides || !flow || !flow_strides || !out) return FLDR_ERR_INVALID_ARGUMENT;
+    if (convention != 0 && convention != 1) return FLDR_ERR_INVALID_ARGUMENT;
     const View4 vx = make_view(x, x_strides), vf = make_view(flow, flow_strides);
     const int st = check_warp_args(N, C, H, W, vx);
     if (st != FLDR_OK) return st;
-    return launch_bwarp<false>(vx, vx, vf, out, N, C, H, W, 0.f, with_mask, reinterpret_cast<cudaStream_t>(stream));
+    return launch_bwarp<false>(vx, vx, vf, out, N, C, H, W, 0.f, with_mask, convention, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int fldr_warp_metric_fwd(const float* ref, const int64_t* ref_strides, const float* src,
@@ -173,5 +197,5 @@ extern "C" int fldr_warp_metric_fwd(const float* ref, const int64_t* ref_strides
     const View4 vr = make_view(ref, ref_strides), vs = make_view(src, src_strides), vf = make_view(flow, flow_strides);
     const int st = check_warp_args(N, C, H, W, vs);
     if (st != FLDR_OK) return st;
-    return launch_bwarp<true>(vs, vr, vf, out, N, C, H, W, alpha, with_mask, reinterpret_cast<cudaStream_t>(stream));
+    return launch_bwarp<true>(vs, vr, vf, out, N, C, H, W, alpha, with_mask, 0, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -3,6 +3,7 @@
 Same call shapes as the reference (file:line = /root/reference/fLDRnet.py):
 
   bwarp(x, flo, withmask=True)                         546-581   DCTVFInet.bwarp as a free function
+  pwc_backward(tensorInput, tensorFlow)                OpticalFlow/PWCNet.py:116-143   the decoder's warp of the second features
   splat_metric(x_ref, x_src, flo, z_alpha, withmask)   442-443   z = mean_c(z_alpha * |x_ref - bwarp(x_src, flo)|)
 
 ``bwarp`` can replace the method without editing fLDRnet.py:  ``DCTVFInet.bwarp = lambda self, x, flo, withmask=True,
@@ -21,8 +22,18 @@ def _check_no_grad(*tensors):
                                   "(the backward of this row is not built yet)")
 
 
+def pwc_backward(tensorInput, tensorFlow):
+    """PWC-Net's ``Backward(tensorInput, tensorFlow, ...)`` (OpticalFlow/PWCNet.py:116-143) without its grid / ones
+    caches: tensorInput sampled at linspace(-1,1)[p] + flow / ((size-1)/2), times the [weight > 0.999] mask."""
+    return _bwarp(tensorInput, tensorFlow, True, 1)
+
+
 def bwarp(x, flo, withmask=True):
     """x [B,C,H,W], flo [B,2,H,W] -> x sampled at (p + flo) with the reference's normalisation, times the 0.999 mask."""
+    return _bwarp(x, flo, withmask, 0)
+
+
+def _bwarp(x, flo, withmask, convention):
     if not x.is_cuda:
         raise NotImplementedError()
     _check_cuda_f32("x", x)
@@ -34,7 +45,7 @@ def bwarp(x, flo, withmask=True):
     out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
     with _device_of(x):
         st = lib.fldr_bwarp_fwd(_lib.ptr(x), _lib.strides(x), _lib.ptr(flo), _lib.strides(flo), _lib.ptr(out),
-                                B, C, H, W, 1 if withmask else 0, _stream_ptr(x.device))
+                                B, C, H, W, 1 if withmask else 0, convention, _stream_ptr(x.device))
     _lib.check(st)
     return out
 

@@ -166,10 +166,14 @@ int fldr_corr81_bwd(const float* first, const int64_t* first_strides,
  *   align_corners=False default, zero padding), iy likewise, times the mask
  *   [sum of in-frame bilinear weights >= 0.999] when with_mask != 0 (569-578).
  *   x [N,C,H,W] with strides (non-negative H/W strides), flow [N,2,H,W] with strides, out [N,C,H,W] contiguous.
+ * convention 0: as above.  convention 1: PWC-Net's Backward (OpticalFlow/PWCNet.py:116-143), the warp of the second
+ *   feature map in front of every correlation: g = linspace(-1,1,W)[x] + u / ((W-1)/2), same
+ *   un-normalisation, mask = [in-frame weight > 0.999] always applied (with_mask is ignored).
  */
 int fldr_bwarp_fwd(const float* x, const int64_t* x_strides,
                    const float* flow, const int64_t* flow_strides,
-                   float* out, int N, int C, int H, int W, int with_mask, fldr_stream_t stream);
+                   float* out, int N, int C, int H, int W, int with_mask, int convention,
+                   fldr_stream_t stream);
 
 /*
  * The splat metric of fLDRnet.py:442-446 in one pass, without materialising the warped image:

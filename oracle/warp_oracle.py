@@ -8,7 +8,7 @@ Follows, explicitly and without calling ``grid_sample``:
     gx = 2*X/max(W-1,1) - 1,  gy = 2*Y/max(H-1,1) - 1         :565-566   (align_corners=True style normalisation ...)
     output = grid_sample(x, grid)                             :568       (... fed to the align_corners=False default:
                                                                           ix = ((gx+1)*W - 1)/2 = X*W/(W-1) - 0.5, a quirk
-                                                                          we preserve)
+                                                                          we preserve; one rounding, see _unnormalise)
     mask = grid_sample(ones, grid); mask<0.999 -> 0; mask>0 -> 1   :569-574
     return output*mask if withmask else output                :578-581
   bilinear, zero padding: taps (floor(ix), floor(iy)) + {0,1}^2 with weights (1-tx)(1-ty) ..., taps outside the
@@ -21,10 +21,42 @@ Pinned against tests/golden/warp_*.npz, which tests/golden/make_golden.py produc
 import torch
 
 
+def _unnormalise(g, size):
+    """grid_sample's align_corners=False un-normalisation ((g + 1) * size - 1) / 2.  torch evaluates it with ONE rounding
+    (a fused multiply-add, on the CPU's vector path and on CUDA alike - established against the golden vectors, which
+    the unfused form misses by an ulp of the coordinate); emulated exactly here by evaluating in float64 (the 24 x 13
+    bit product is exact there) and rounding once."""
+    return (((g + 1.0).double() * size - 1.0) / 2.0).float()
+
+
 def _source_index(coord, size):
-    """fLDRnet.py:565-566 followed by grid_sample's align_corners=False un-normalisation, in fp32 and in that order."""
+    """fLDRnet.py:565-566 in float32, operation by operation, followed by grid_sample's un-normalisation."""
     g = 2.0 * coord / max(size - 1, 1) - 1.0
-    return ((g + 1.0) * size - 1.0) / 2.0
+    return _unnormalise(g, size)
+
+
+def _linspace_pm1(n):
+    """torch.linspace(-1, 1, n) on the CPU, restated: float32 step, one fused multiply-add per element, mirrored halves
+    (the fused rounding is emulated exactly by evaluating in float64 and rounding once: step*i has at most 48 bits)."""
+    if n == 1:
+        return torch.tensor([-1.0])
+    step = (torch.tensor(2.0) / torch.tensor(float(n - 1))).double()
+    i = torch.arange(n, dtype=torch.float64)
+    lo = (-1.0 + step * i).float()
+    hi = (1.0 - step * (n - 1 - i)).float()
+    return torch.where(torch.arange(n) < n // 2, lo, hi)
+
+
+def pwc_backward(x, flo, return_mask=False):
+    """PWC-Net's Backward (OpticalFlow/PWCNet.py:116-143): grid = linspace(-1,1) per axis (:117-130), flow divided by
+    (size-1)/2 (:134-135), grid_sample bilinear / zeros / align_corners=False default of the input with a ones channel
+    (:136-138), mask = [ones channel > 0.999] (:140-141), output * mask (:143)."""
+    x = x.float()
+    flo = flo.float()
+    B, C, H, W = x.shape
+    gx = _linspace_pm1(W).view(1, 1, W) + flo[:, 0] / ((W - 1.0) / 2.0)
+    gy = _linspace_pm1(H).view(1, H, 1) + flo[:, 1] / ((H - 1.0) / 2.0)
+    return _sample(x, _unnormalise(gx, W), _unnormalise(gy, H), True, return_mask, strict=True)
 
 
 def bwarp(x, flo, withmask=True, return_mask=False):
@@ -35,6 +67,11 @@ def bwarp(x, flo, withmask=True, return_mask=False):
     yy = torch.arange(H, dtype=torch.float32).view(1, H, 1).expand(B, H, W)
     ix = _source_index(xx + flo[:, 0], W)
     iy = _source_index(yy + flo[:, 1], H)
+    return _sample(x, ix, iy, withmask, return_mask, strict=False)
+
+
+def _sample(x, ix, iy, withmask, return_mask, strict):
+    B, C, H, W = x.shape
     x0 = torch.floor(ix)
     y0 = torch.floor(iy)
     x1 = x0 + 1
@@ -52,7 +89,8 @@ def bwarp(x, flo, withmask=True, return_mask=False):
         wk = torch.where(ok, w, torch.zeros_like(w))
         out = out + v * wk.unsqueeze(1)
         msum = msum + wk
-    mask = (msum >= 0.999).float().unsqueeze(1)          # <0.999 -> 0, every survivor (>0) -> 1
+    # fLDRnet: <0.999 -> 0, every survivor (>0) -> 1;  PWC-Net: >0.999 -> 1, everything else (<1) -> 0
+    mask = ((msum > 0.999) if strict else (msum >= 0.999)).float().unsqueeze(1)
     res = out * mask if withmask else out
     return (res, msum) if return_mask else res
 

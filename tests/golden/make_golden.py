@@ -102,6 +102,25 @@ def warp_case(name, N, C, H, W, regime, scale, seed, alpha=-1.894):
     print(name, tuple(out["bwarp_mask"].shape), "masked px", int((out["bwarp_mask"].abs().sum(1) == 0).sum()))
 
 
+def pwcwarp_case(name, N, C, H, W, regime, scale, seed):
+    """PWC-Net's own ``Backward`` source (OpticalFlow/PWCNet.py:116-143), lifted by ast.  The only edit is dropping the
+    ``.cuda()`` of line 130: the reference builds its linspace grid on the CPU and then moves it, so the CPU values are
+    the ones that count."""
+    import ast
+    import textwrap
+    src = open("/root/reference/OpticalFlow/PWCNet.py").read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "Backward")
+    code = textwrap.dedent("\n".join(src.splitlines()[fn.lineno - 1:fn.end_lineno])).replace(".cuda()", "")
+    ns = {"torch": torch}
+    exec(compile(code, "PWCNet.py:Backward", "exec"), ns)
+    x = synth.features(N, C, H, W, seed=seed)
+    fl = synth.flow(N, H, W, regime, seed=seed + 1) * scale
+    with torch.no_grad():
+        out = ns["Backward"](None, x, fl.clone(), {}, {})
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), input=x.numpy(), flow=fl.numpy(), out=out.numpy())
+    print(name, tuple(out.shape), "masked px", int((out.abs().sum(1) == 0).sum()))
+
+
 def _reference_blend_lines():
     """fLDRnet.py's own source lines from ``num_softmax_combs = 6`` to ``out_l /=divisor`` (510-524), dedented."""
     import textwrap
@@ -136,6 +155,11 @@ if __name__ == "__main__":
         blend_case("blend_t05", 2, 3, 16, 24, 210)                       # t = 0.5 / 0.55, T = 1 (the shipped checkpoint)
         blend_case("blend_temp", 1, 3, 9, 13, 220, temperature=0.37, t=0.25)   # odd sizes, learned temperature, t != 0.5
         blend_case("blend_c1", 3, 1, 8, 8, 230, temperature=2.0, t=0.8)
+        sys.exit(0)
+    if "--pwcwarp-only" in sys.argv:
+        pwcwarp_case("pwcwarp_smooth", 2, 5, 24, 40, "F1", 10.0, 310)
+        pwcwarp_case("pwcwarp_scatter", 1, 3, 17, 23, "F2", 1.0, 320)
+        pwcwarp_case("pwcwarp_border", 2, 4, 20, 64, "FB", 1.0, 330)
         sys.exit(0)
     if "--warp-only" in sys.argv:
         warp_case("warp_smooth", 2, 3, 24, 40, "F1", 40.0, 110)     # image-like, smooth large flow

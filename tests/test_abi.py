@@ -92,11 +92,12 @@ def test_argument_validation_needs_no_device(lib):
     assert lib.fldr_corr81_fwd_act(p, s4, p, s4, p, 0, float("nan"), 1, 4, 8, 8, None) == -1
     assert lib.fldr_corr81_fwd_act(p, s4, None, s4, p, 0, 0.1, 1, 4, 8, 8, None) == -1
     # backward warp / splat metric (next row)
-    assert lib.fldr_bwarp_fwd(None, s4, p, s4, p, 1, 3, 8, 8, 1, None) == -1
-    assert lib.fldr_bwarp_fwd(p, s4, p, s4, p, 1, 0, 8, 8, 1, None) == -1
-    assert lib.fldr_bwarp_fwd(p, s4, p, s4, p, 1, 3, 65536, 65536, 1, None) == -4
+    assert lib.fldr_bwarp_fwd(None, s4, p, s4, p, 1, 3, 8, 8, 1, 0, None) == -1
+    assert lib.fldr_bwarp_fwd(p, s4, p, s4, p, 1, 0, 8, 8, 1, 0, None) == -1
+    assert lib.fldr_bwarp_fwd(p, s4, p, s4, p, 1, 3, 65536, 65536, 1, 0, None) == -4
     neg = (ctypes.c_int64 * 4)(64, 64, -8, 1)
-    assert lib.fldr_bwarp_fwd(p, neg, p, s4, p, 1, 3, 8, 8, 1, None) == -4          # flipped views are refused, not mis-read
+    assert lib.fldr_bwarp_fwd(p, neg, p, s4, p, 1, 3, 8, 8, 1, 0, None) == -4       # flipped views are refused, not mis-read
+    assert lib.fldr_bwarp_fwd(p, s4, p, s4, p, 1, 3, 8, 8, 1, 7, None) == -1          # unknown convention
     assert lib.fldr_warp_metric_fwd(p, s4, None, s4, p, s4, 1.0, p, 1, 3, 8, 8, 1, None) == -1
     assert lib.fldr_warp_metric_fwd(p, s4, p, s4, p, s4, 1.0, p, 1, 3, 8, 0, 1, None) == -1
     # occlusion softmax + blend (next row 2)

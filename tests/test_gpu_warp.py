@@ -56,6 +56,26 @@ def test_vs_oracle_shapes(cuda_lib, N, C, H, W, regime, scale):
                tol=4e-6, mask_sum=msum)
 
 
+@pytest.mark.parametrize("name", ["pwcwarp_smooth", "pwcwarp_scatter", "pwcwarp_border"])
+def test_pwc_backward_vs_golden(cuda_lib, name):
+    Wp = _mod(cuda_lib)
+    g = load_golden(name)
+    with torch.no_grad():
+        got = Wp.pwc_backward(g["input"].cuda(), g["flow"].cuda())
+    _close(got, g["out"], name, tol=1e-6 * max(1.0, float(g["out"].abs().max())))
+
+
+@pytest.mark.parametrize("N,C,H,W,scale", [(2, 32, 36, 64, 3.0), (1, 196, 9, 16, 1.0), (1, 7, 33, 47, 6.0), (2, 64, 72, 128, 10.0)])
+def test_pwc_backward_vs_oracle_shapes(cuda_lib, N, C, H, W, scale):
+    Wp = _mod(cuda_lib)
+    x = synth.features(N, C, H, W, seed=21)
+    fl = synth.flow(N, H, W, "F1", seed=22) * scale
+    want, msum = wo.pwc_backward(x, fl, return_mask=True)
+    with torch.no_grad():
+        got = Wp.pwc_backward(x.cuda(), fl.cuda())
+    _close(got, want, "pwc backward", tol=1e-6 * max(1.0, float(want.abs().max())), mask_sum=msum)
+
+
 def test_strided_views_and_nonfinite_flow(cuda_lib):
     Wp = _mod(cuda_lib)
     N, C, H, W = 2, 3, 20, 28

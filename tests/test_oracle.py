@@ -156,6 +156,25 @@ def test_warp_oracle_vs_golden(name):
     assert bool((kept_ref == kept_got).all())
 
 
+PWCWARP_CASES = ["pwcwarp_smooth", "pwcwarp_scatter", "pwcwarp_border"]
+
+
+@pytest.mark.parametrize("name", PWCWARP_CASES)
+def test_pwc_backward_oracle_vs_golden(name):
+    """PWC-Net's Backward restated, against the outputs of its own source (OpticalFlow/PWCNet.py:116-143)."""
+    from oracle import warp_oracle as wo
+    g = load_golden(name)
+    got = wo.pwc_backward(g["input"], g["flow"])
+    assert float((got - g["out"]).abs().max()) <= 1e-6 * max(1.0, float(g["out"].abs().max()))
+    assert bool(((got.abs().sum(1) > 0) == (g["out"].abs().sum(1) > 0)).all())
+
+
+def test_linspace_restatement_is_bit_exact():
+    from oracle import warp_oracle as wo
+    for n in (1, 2, 3, 17, 23, 40, 64, 288, 1024, 2304, 4096):
+        assert bool((wo._linspace_pm1(n) == torch.linspace(-1.0, 1.0, n)).all()), n
+
+
 def test_warp_kat_zero_flow_is_not_identity_but_integer_grid_is():
     """Reference quirk (fLDRnet.py:565-568): coordinates are normalised with W-1 and sampled with align_corners=False,
     so zero flow resamples at X*W/(W-1) - 0.5.  A flow of u = (x + 0.5)*(W-1)/W - x undoes it exactly."""
