@@ -11,4 +11,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:"spl
 timeout 900 python baseline/e2e_fldrnet.py --reps 3 > gpurun_out/e2e_fldrnet.json 2> gpurun_out/e2e.err
 timeout 600 python tools/bench_bwd.py > gpurun_out/bwd_training_shapes.txt 2>&1
 timeout 300 python tools/overhead_probe.py > gpurun_out/host_overhead.txt 2>&1
+timeout 200 python tools/warp_probe.py > gpurun_out/warp_probe.txt 2>&1
+timeout 200 python tools/blend_probe.py > gpurun_out/blend_probe.txt 2>&1
+timeout 200 python tools/corr_act_probe.py > gpurun_out/corr_act_probe.txt 2>&1
 tail -c 600 gpurun_out/bench_full.json; echo; tail -c 400 gpurun_out/e2e_fldrnet.json
