@@ -66,14 +66,8 @@ def worker(impl, out_path, reps, height, width):
         # next row: replace the bwarp METHOD on the imported class - fLDRnet.py itself stays untouched
         import fLDRnet
         sys.path.insert(0, ROOT)
-        from fldr_vfi_b200.warp import bwarp as fast_bwarp
-        ref_bwarp = fLDRnet.DCTVFInet.bwarp
-
-        def patched(self, x, flo, withmask=True, minus=False):
-            if x.dtype != torch.float32 or flo.dtype != torch.float32 or not x.is_cuda or torch.is_grad_enabled():
-                return ref_bwarp(self, x, flo, withmask, minus)      # the reference's own path for what this row does not cover
-            return fast_bwarp(x, flo, withmask)
-        fLDRnet.DCTVFInet.bwarp = patched
+        from fldr_vfi_b200.integrate import patch_bwarp
+        patch_bwarp(fLDRnet)
         which += " + fldr_vfi_b200.warp.bwarp"
     model_net, device, args = R.prepare_model()
     model_net.eval()

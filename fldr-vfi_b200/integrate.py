@@ -1,0 +1,31 @@
+"""Optional run-time hooks that route more of the reference's forward pass through the sm_100a library without editing
+a reference file.  The import-name drop-ins (``dropin/``) need none of this; see INTEGRATION.md.
+
+    import fLDRnet                         # the reference's module, untouched
+    from fldr_vfi_b200.integrate import patch_bwarp
+    patch_bwarp(fLDRnet)                   # DCTVFInet.bwarp -> fldr_bwarp_fwd for float32 CUDA tensors under no_grad
+"""
+import torch
+
+from .warp import bwarp as _fast_bwarp
+
+
+def patch_bwarp(fldrnet_module):
+    """Replace ``DCTVFInet.bwarp`` (fLDRnet.py:546-581) by the fused gather kernel.  Calls the replacement does not cover
+    (training / autograd, non-float32, CPU tensors) go to the reference's own method, so behaviour there is unchanged.
+    Returns the original method (assign it back to undo)."""
+    cls = fldrnet_module.DCTVFInet
+    original = cls.bwarp
+    if getattr(original, "_fldr_b200_patched", False):
+        return original._fldr_b200_original
+
+    def bwarp(self, x, flo, withmask=True, minus=False):
+        if (torch.is_grad_enabled() and (x.requires_grad or flo.requires_grad)) or not x.is_cuda \
+                or x.dtype != torch.float32 or flo.dtype != torch.float32:
+            return original(self, x, flo, withmask, minus)
+        return _fast_bwarp(x, flo, withmask)
+
+    bwarp._fldr_b200_patched = True
+    bwarp._fldr_b200_original = original
+    cls.bwarp = bwarp
+    return original

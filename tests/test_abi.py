@@ -135,6 +135,25 @@ def test_host_mirror_names_and_cpu_errors(lib):
         Bl.occ_blend(torch.zeros(1, 6, 4, 4), torch.ones(1, dtype=torch.float64), torch.full((1, 1), 0.5), x, x, x, x, x, x)
 
 
+def test_patch_bwarp_routes_only_what_the_kernel_covers(lib):
+    """integrate.patch_bwarp swaps the method on a class and leaves CPU / autograd calls to the original."""
+    import types
+    from fldr_vfi_b200.integrate import patch_bwarp
+    calls = []
+
+    class DCTVFInet:
+        def bwarp(self, x, flo, withmask=True, minus=False):
+            calls.append("reference")
+            return x
+    mod = types.SimpleNamespace(DCTVFInet=DCTVFInet)
+    original = patch_bwarp(mod)
+    assert patch_bwarp(mod) is original                          # idempotent
+    x, fl = torch.zeros(1, 3, 4, 4), torch.zeros(1, 2, 4, 4)
+    assert DCTVFInet().bwarp(x, fl) is x and calls == ["reference"]      # CPU tensor -> the reference's own method
+    DCTVFInet.bwarp = original
+    assert not getattr(DCTVFInet.bwarp, "_fldr_b200_patched", False)
+
+
 def test_dropin_import_names_shadow_reference_modules(lib):
     """`from softSplat import Softsplat` (fLDRnet.py:22) and `from . import correlation` inside the OpticalFlow
     namespace package (PWCNet.py:4) resolve to the drop-ins when dropin/ is first on sys.path.  Importing the
