@@ -41,6 +41,9 @@ SYMBOLS = {
     "fldr_bwarp_fwd": (ctypes.c_int, [c_float_p, c_i64_p, c_float_p, c_i64_p, c_float_p,
                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_void_p]),
+    "fldr_bwarp_bwd": (ctypes.c_int, [c_float_p, c_i64_p, c_float_p, c_i64_p, c_float_p, c_i64_p, c_float_p, c_float_p,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_void_p]),
     "fldr_warp_metric_fwd": (ctypes.c_int, [c_float_p, c_i64_p, c_float_p, c_i64_p, c_float_p, c_i64_p, ctypes.c_float,
                                             c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_void_p]),

@@ -166,6 +166,55 @@ static int launch_bwarp(const View4& src, const View4& ref, const View4& flow, f
     return FLDR_OK;
 }
 
+// Backward of the warp (autograd of fLDRnet.py:556-578 / PWCNet.py:134-143; the mask is piecewise constant and
+// carries no gradient, floor() neither):
+//   grad_x[c, tap_k]  += keep * w_k * g[c]                                  (scatter, red.global.add.f32)
+//   d out / d ix = keep * sum_c g[c] * ((x_ne - x_nw) * (y1 - iy) + (x_se - x_sw) * (iy - y0))      taps outside = 0
+//   d out / d iy = keep * sum_c g[c] * ((x_sw - x_nw) * (x1 - ix) + (x_se - x_ne) * (ix - x0))
+//   grad_flow = (d/d ix * W/(W-1), d/d iy * H/(H-1))        both conventions: (2/(W-1)) * (W/2)
+// One thread per pixel, channel loop; grad_x is zero-filled by the entry point.
+__global__ void __launch_bounds__(128) bwarp_bwd_kernel(View4 src, View4 flow, View4 gout, float* __restrict__ grad_x,
+                                                        float* __restrict__ grad_flow, int C, int H, int W, int with_mask,
+                                                        int y_base, int convention) {
+    const int x = blockIdx.x * 128 + threadIdx.x, y = y_base + blockIdx.y, n = blockIdx.z;
+    if (x >= W) return;
+    const long long HW = (long long)H * W, idx = (long long)y * W + x;
+    const float* fp = flow.p + n * flow.sn + y * flow.sh + x * flow.sw;
+    const float u = __ldg(fp), v = __ldg(fp + flow.sc);
+    // taps relative to a CONTIGUOUS plane for grad_x (sh = W, sw = 1) and to the source view for the x reads
+    const WarpTaps ts = warp_taps(u, v, x, y, H, W, (int)src.sh, (int)src.sw, with_mask != 0, convention);
+    const WarpTaps tg = warp_taps(u, v, x, y, H, W, W, 1, with_mask != 0, convention);
+    const float ix = warp_source_index(x, u, W, convention), iy = warp_source_index(y, v, H, convention);
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const float ax = ix - fx0, bx = (fx0 + 1.0f) - ix, ay = iy - fy0, by = (fy0 + 1.0f) - iy;
+    const float* gp = gout.p + n * gout.sn + y * gout.sh + x * gout.sw;
+    const float* sp = src.p + n * src.sn;
+    float dix = 0.f, diy = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const float g = ts.keep ? __ldg(gp + c * gout.sc) : 0.f;
+        if (grad_x) {
+            float* gx = grad_x + ((long long)n * C + c) * HW;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (tg.keepbits[k] && g != 0.f) atomicAdd(gx + tg.off[k], g * tg.w[k]);
+        }
+        if (grad_flow) {
+            const float* plane = sp + (long long)c * src.sc;
+            float t[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] = __uint_as_float(__float_as_uint(__ldg(plane + ts.off[k])) & ts.keepbits[k]);
+            dix += g * ((t[1] - t[0]) * by + (t[3] - t[2]) * ay);
+            diy += g * ((t[2] - t[0]) * bx + (t[3] - t[1]) * ax);
+        }
+    }
+    if (grad_flow) {
+        const bool finite = (ix == ix) && (iy == iy) && fabsf(ix) < 3.0e38f && fabsf(iy) < 3.0e38f;
+        float* gf = grad_flow + (long long)n * 2 * HW + idx;
+        gf[0] = finite ? dix * ((float)W / (float)max(W - 1, 1)) : 0.f;
+        gf[HW] = finite ? diy * ((float)H / (float)max(H - 1, 1)) : 0.f;
+    }
+}
+
 static int check_warp_args(int N, int C, int H, int W, const View4& src) {
     if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return FLDR_ERR_INVALID_ARGUMENT;
     if ((long long)H * W >= (1ll << 31) || N > 65535) return FLDR_ERR_UNSUPPORTED;
@@ -198,4 +247,28 @@ extern "C" int fldr_warp_metric_fwd(const float* ref, const int64_t* ref_strides
     const int st = check_warp_args(N, C, H, W, vs);
     if (st != FLDR_OK) return st;
     return launch_bwarp<true>(vs, vr, vf, out, N, C, H, W, alpha, with_mask, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fldr_bwarp_bwd(const float* x, const int64_t* x_strides, const float* flow, const int64_t* flow_strides,
+                              const float* grad_out, const int64_t* grad_out_strides, float* grad_x, float* grad_flow,
+                              int N, int C, int H, int W, int with_mask, int convention, fldr_stream_t stream) {
+    if (!x || !x_strides || !flow || !flow_strides || !grad_out || !grad_out_strides) return FLDR_ERR_INVALID_ARGUMENT;
+    if (convention != 0 && convention != 1) return FLDR_ERR_INVALID_ARGUMENT;
+    const View4 vx = make_view(x, x_strides), vf = make_view(flow, flow_strides), vg = make_view(grad_out, grad_out_strides);
+    const int st = check_warp_args(N, C, H, W, vx);
+    if (st != FLDR_OK) return st;
+    if (!grad_x && !grad_flow) return FLDR_OK;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (grad_x) {
+        const cudaError_t e = cudaMemsetAsync(grad_x, 0, (size_t)N * C * H * W * sizeof(float), s);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
+    }
+    for (int y0 = 0; y0 < H; y0 += 65535) {
+        const int rows = H - y0 < 65535 ? H - y0 : 65535;
+        dim3 grid((unsigned)((W + 127) / 128), (unsigned)rows, (unsigned)N);
+        bwarp_bwd_kernel<<<grid, 128, 0, s>>>(vx, vf, vg, grad_x, grad_flow, C, H, W, with_mask, y0, convention);
+        const int st2 = check_launch();
+        if (st2 != FLDR_OK) return st2;
+    }
+    return FLDR_OK;
 }

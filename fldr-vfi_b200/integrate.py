@@ -3,7 +3,7 @@ a reference file.  The import-name drop-ins (``dropin/``) need none of this; see
 
     import fLDRnet                         # the reference's module, untouched
     from fldr_vfi_b200.integrate import patch_bwarp
-    patch_bwarp(fLDRnet)                   # DCTVFInet.bwarp -> fldr_bwarp_fwd for float32 CUDA tensors under no_grad
+    patch_bwarp(fLDRnet)                   # DCTVFInet.bwarp -> fldr_bwarp_fwd / fldr_bwarp_bwd for float32 CUDA tensors
 """
 import torch
 
@@ -11,8 +11,8 @@ from .warp import bwarp as _fast_bwarp
 
 
 def patch_bwarp(fldrnet_module):
-    """Replace ``DCTVFInet.bwarp`` (fLDRnet.py:546-581) by the fused gather kernel.  Calls the replacement does not cover
-    (training / autograd, non-float32, CPU tensors) go to the reference's own method, so behaviour there is unchanged.
+    """Replace ``DCTVFInet.bwarp`` (fLDRnet.py:546-581) by the fused gather kernel (forward and backward).  Calls the
+    replacement does not cover (non-float32, CPU tensors) go to the reference's own method, so behaviour there is unchanged.
     Returns the original method (assign it back to undo)."""
     cls = fldrnet_module.DCTVFInet
     original = cls.bwarp
@@ -20,8 +20,7 @@ def patch_bwarp(fldrnet_module):
         return original._fldr_b200_original
 
     def bwarp(self, x, flo, withmask=True, minus=False):
-        if (torch.is_grad_enabled() and (x.requires_grad or flo.requires_grad)) or not x.is_cuda \
-                or x.dtype != torch.float32 or flo.dtype != torch.float32:
+        if not x.is_cuda or x.dtype != torch.float32 or flo.dtype != torch.float32:
             return original(self, x, flo, withmask, minus)
         return _fast_bwarp(x, flo, withmask)
 

@@ -6,9 +6,9 @@ Same call shapes as the reference (file:line = /root/reference/fLDRnet.py):
   pwc_backward(tensorInput, tensorFlow)                OpticalFlow/PWCNet.py:116-143   the decoder's warp of the second features
   splat_metric(x_ref, x_src, flo, z_alpha, withmask)   442-443   z = mean_c(z_alpha * |x_ref - bwarp(x_src, flo)|)
 
-``bwarp`` can replace the method without editing fLDRnet.py:  ``DCTVFInet.bwarp = lambda self, x, flo, withmask=True,
-minus=False: bwarp(x, flo, withmask)``.  Forward only in this round: tensors that require grad
-while grad mode is on raise instead of silently detaching (training keeps the reference's torch path).
+``bwarp`` can replace the method without editing fLDRnet.py (``fldr_vfi_b200.integrate.patch_bwarp``).
+``bwarp`` / ``pwc_backward`` are differentiable (``fldr_bwarp_bwd``: gradients w.r.t. the image and the flow);
+``splat_metric`` is forward only: tensors that require grad while grad mode is on raise instead of silently detaching.
 """
 import torch
 
@@ -18,8 +18,8 @@ from .softSplat import _check_cuda_f32, _device_of, _stream_ptr
 
 def _check_no_grad(*tensors):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
-        raise NotImplementedError("fldr_b200 bwarp / splat_metric are forward-only: call under torch.no_grad() "
-                                  "(the backward of this row is not built yet)")
+        raise NotImplementedError("this fldr_b200 entry point is forward-only: call it under torch.no_grad() "
+                                  "(its backward is not built yet)")
 
 
 def pwc_backward(tensorInput, tensorFlow):
@@ -33,12 +33,43 @@ def bwarp(x, flo, withmask=True):
     return _bwarp(x, flo, withmask, 0)
 
 
+class _FunctionBwarp(torch.autograd.Function):
+    """Autograd wrapper: backward = fldr_bwarp_bwd, one launch for the requested gradients (the 0.999 mask and floor()
+    carry no gradient, exactly as in the graph autograd builds for the reference)."""
+
+    @staticmethod
+    def forward(ctx, x, flo, withmask, convention):
+        ctx.save_for_backward(x, flo)
+        ctx.withmask, ctx.convention = withmask, convention
+        return _bwarp_forward(x, flo, withmask, convention)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, flo = ctx.saved_tensors
+        _check_cuda_f32("grad_out", grad_out)
+        B, C, H, W = x.shape
+        gx = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
+        gf = torch.empty((B, 2, H, W), dtype=torch.float32, device=x.device) if ctx.needs_input_grad[1] else None
+        lib = _lib.lib()
+        with _device_of(x):
+            st = lib.fldr_bwarp_bwd(_lib.ptr(x), _lib.strides(x), _lib.ptr(flo), _lib.strides(flo), _lib.ptr(grad_out),
+                                    _lib.strides(grad_out), _lib.ptr(gx), _lib.ptr(gf), B, C, H, W,
+                                    1 if ctx.withmask else 0, ctx.convention, _stream_ptr(x.device))
+        _lib.check(st)
+        return gx, gf, None, None
+
+
 def _bwarp(x, flo, withmask, convention):
     if not x.is_cuda:
         raise NotImplementedError()
     _check_cuda_f32("x", x)
     _check_cuda_f32("flo", flo)
-    _check_no_grad(x, flo)
+    if torch.is_grad_enabled() and (x.requires_grad or flo.requires_grad):
+        return _FunctionBwarp.apply(x, flo, bool(withmask), convention)
+    return _bwarp_forward(x, flo, withmask, convention)
+
+
+def _bwarp_forward(x, flo, withmask, convention):
     B, C, H, W = x.shape
     assert flo.shape == (B, 2, H, W)
     lib = _lib.lib()

@@ -176,6 +176,17 @@ int fldr_bwarp_fwd(const float* x, const int64_t* x_strides,
                    fldr_stream_t stream);
 
 /*
+ * Backward of fldr_bwarp_fwd (what autograd derives for fLDRnet.py:556-578 / PWCNet.py:134-143; the mask and floor()
+ * carry no gradient).  grad_out [N,C,H,W] with strides; grad_x [N,C,H,W] contiguous (zero-filled here, then
+ * accumulated) and grad_flow [N,2,H,W] contiguous; either may be NULL.
+ */
+int fldr_bwarp_bwd(const float* x, const int64_t* x_strides,
+                   const float* flow, const int64_t* flow_strides,
+                   const float* grad_out, const int64_t* grad_out_strides,
+                   float* grad_x, float* grad_flow,
+                   int N, int C, int H, int W, int with_mask, int convention, fldr_stream_t stream);
+
+/*
  * The splat metric of fLDRnet.py:442-446 in one pass, without materialising the warped image:
  *   out[n,0,y,x] = (1/C) * sum_c alpha * | ref[n,c,y,x] - bwarp(src, flow)[n,c,y,x] |
  *   ref, src [N,C,H,W] with strides; out [N,1,H,W] contiguous; alpha = z_alpha[i] rounded to fp32.

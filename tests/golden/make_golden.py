@@ -98,6 +98,11 @@ def warp_case(name, N, C, H, W, regime, scale, seed, alpha=-1.894):
         z_alpha = torch.tensor([alpha, alpha], dtype=torch.float64)          # fLDRnet.py:360: a double Parameter
         out["metric"] = torch.mean(z_alpha[0] * torch.abs(x0 - out["bwarp_mask"]), dim=1, keepdim=True)   # fLDRnet.py:443
     assert out["metric"].dtype == torch.float32
+    # gradients of the reference's own bwarp by autograd (grid_sample backward on the CPU)
+    g = synth.grad((N, C, H, W), seed=seed + 3)
+    xi, fi = x1.clone().requires_grad_(True), fl.clone().requires_grad_(True)
+    gx, gf = torch.autograd.grad(bwarp(xi, fi, True), [xi, fi], g)
+    out["grad_out"], out["grad_src"], out["grad_flow"] = g, gx, gf
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **{k: v.numpy() for k, v in out.items()})
     print(name, tuple(out["bwarp_mask"].shape), "masked px", int((out["bwarp_mask"].abs().sum(1) == 0).sum()))
 

@@ -98,6 +98,8 @@ def test_argument_validation_needs_no_device(lib):
     neg = (ctypes.c_int64 * 4)(64, 64, -8, 1)
     assert lib.fldr_bwarp_fwd(p, neg, p, s4, p, 1, 3, 8, 8, 1, 0, None) == -4       # flipped views are refused, not mis-read
     assert lib.fldr_bwarp_fwd(p, s4, p, s4, p, 1, 3, 8, 8, 1, 7, None) == -1          # unknown convention
+    assert lib.fldr_bwarp_bwd(p, s4, p, s4, None, s4, p, p, 1, 3, 8, 8, 1, 0, None) == -1
+    assert lib.fldr_bwarp_bwd(p, s4, p, s4, p, s4, p, p, 1, 3, 8, 8, 1, 2, None) == -1
     assert lib.fldr_warp_metric_fwd(p, s4, None, s4, p, s4, 1.0, p, 1, 3, 8, 8, 1, None) == -1
     assert lib.fldr_warp_metric_fwd(p, s4, p, s4, p, s4, 1.0, p, 1, 3, 8, 0, 1, None) == -1
     # occlusion softmax + blend (next row 2)

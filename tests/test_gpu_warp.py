@@ -91,12 +91,51 @@ def test_strided_views_and_nonfinite_flow(cuda_lib):
     assert float(got[0, :, 3, 4].abs().max()) == 0.0 and float(got[1, :, 5, 6].abs().max()) == 0.0   # sampled nothing
 
 
-def test_requires_grad_is_refused_not_detached(cuda_lib):
+def _grad_close(got, ref, what):
+    err = float((got.detach().cpu().double() - ref.double()).abs().max())
+    tol = 1e-5 * max(1.0, float(ref.abs().max()))            # atomics: summation order differs from the CPU's
+    assert err <= tol, f"{what}: max err {err:.3e} > {tol:.3e}"
+
+
+@pytest.mark.parametrize("name", WARP_CASES)
+def test_gradients_vs_golden(cuda_lib, name):
+    """fldr_bwarp_bwd against autograd through the reference's own bwarp (golden, CPU grid_sample backward)."""
+    Wp = _mod(cuda_lib)
+    g = load_golden(name)
+    xi, fi = g["src"].cuda().requires_grad_(True), g["flow"].cuda().requires_grad_(True)
+    out = Wp.bwarp(xi, fi, True)
+    gx, gf = torch.autograd.grad(out, [xi, fi], g["grad_out"].cuda())
+    _grad_close(gx, g["grad_src"], name + " grad_x")
+    _grad_close(gf, g["grad_flow"], name + " grad_flow")
+
+
+@pytest.mark.parametrize("conv,N,C,H,W,scale", [(0, 2, 3, 40, 56, 20.0), (0, 1, 5, 17, 23, 3.0), (1, 2, 32, 36, 64, 3.0), (1, 1, 7, 9, 16, 1.0)])
+def test_gradients_vs_oracle_autograd(cuda_lib, conv, N, C, H, W, scale):
+    Wp = _mod(cuda_lib)
+    x = synth.features(N, C, H, W, seed=31)
+    fl = synth.flow(N, H, W, "F1", seed=32) * scale
+    go = synth.grad((N, C, H, W), seed=33)
+    xo, fo = x.clone().requires_grad_(True), fl.clone().requires_grad_(True)
+    ref = wo.bwarp(xo, fo, True) if conv == 0 else wo.pwc_backward(xo, fo)
+    gxo, gfo = torch.autograd.grad(ref, [xo, fo], go)
+    xd, fd = x.cuda().requires_grad_(True), fl.cuda().requires_grad_(True)
+    out = Wp.bwarp(xd, fd, True) if conv == 0 else Wp.pwc_backward(xd, fd)
+    gx, gf = torch.autograd.grad(out, [xd, fd], go.cuda())
+    _grad_close(gx, gxo, "grad_x")
+    _grad_close(gf, gfo, "grad_flow")
+    # needs_input_grad is honoured: only the flow gradient requested
+    fd2 = fl.cuda().requires_grad_(True)
+    out2 = Wp.bwarp(x.cuda(), fd2, True) if conv == 0 else Wp.pwc_backward(x.cuda(), fd2)
+    (gf2,) = torch.autograd.grad(out2, [fd2], go.cuda())
+    _grad_close(gf2, gfo, "grad_flow only")
+
+
+def test_metric_is_forward_only_and_dtype_checked(cuda_lib):
     Wp = _mod(cuda_lib)
     x = torch.zeros(1, 3, 8, 8, device="cuda", requires_grad=True)
     fl = torch.zeros(1, 2, 8, 8, device="cuda")
     with pytest.raises(NotImplementedError):
-        Wp.bwarp(x, fl)
+        Wp.splat_metric(x, x, fl, -1.9)
     with torch.no_grad():
         assert Wp.bwarp(x, fl).shape == (1, 3, 8, 8)
     with pytest.raises(TypeError):

@@ -156,6 +156,18 @@ def test_warp_oracle_vs_golden(name):
     assert bool((kept_ref == kept_got).all())
 
 
+@pytest.mark.parametrize("name", WARP_CASES)
+def test_warp_oracle_gradients_vs_golden(name):
+    """Autograd through the explicit restatement against autograd through the reference's own bwarp (grid_sample
+    backward), both on the CPU."""
+    from oracle import warp_oracle as wo
+    g = load_golden(name)
+    xi, fi = g["src"].clone().requires_grad_(True), g["flow"].clone().requires_grad_(True)
+    gx, gf = torch.autograd.grad(wo.bwarp(xi, fi, True), [xi, fi], g["grad_out"])
+    assert float((gx - g["grad_src"]).abs().max()) <= 2e-6 * max(1.0, float(g["grad_src"].abs().max()))
+    assert float((gf - g["grad_flow"]).abs().max()) <= 2e-6 * max(1.0, float(g["grad_flow"].abs().max()))
+
+
 PWCWARP_CASES = ["pwcwarp_smooth", "pwcwarp_scatter", "pwcwarp_border"]
 
 
