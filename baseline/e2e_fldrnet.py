@@ -71,6 +71,10 @@ def worker(impl, out_path, reps, height, width):
         which += " + fldr_vfi_b200.warp.bwarp"
     model_net, device, args = R.prepare_model()
     model_net.eval()
+    if impl == "ours_warp":
+        from fldr_vfi_b200.integrate import patch_pwc_backward
+        n_pwc = patch_pwc_backward(model_net)
+        which += f" + pwc_backward on {n_pwc} decoder modules"
     frames = synthetic_triplet(height, width)
     t_value = torch.tensor([[0.5]])
     times = []

@@ -28,3 +28,29 @@ def patch_bwarp(fldrnet_module):
     bwarp._fldr_b200_original = original
     cls.bwarp = bwarp
     return original
+
+
+def patch_pwc_backward(model):
+    """Route every ``Backward(tensorInput, tensorFlow, grid_cache, ones_cache)`` method found on the sub-modules of a
+    built model (PWC-Net's decoders, OpticalFlow/PWCNet.py:116-143 - the classes are local to ``Network.__init__``, so
+    the instances are patched) through ``fldr_bwarp_fwd`` convention 1.  Returns the number of modules patched."""
+    import types
+
+    from .warp import pwc_backward
+
+    count = 0
+    for m in model.modules():
+        original = getattr(m, "Backward", None)
+        if original is None or getattr(original, "_fldr_b200_patched", False) or not callable(original):
+            continue
+
+        def Backward(self, tensorInput, tensorFlow, Backward_tensorGrid=None, Backward_tensorPartial=None, _orig=original):
+            if not tensorInput.is_cuda or tensorInput.dtype != torch.float32 or tensorFlow.dtype != torch.float32:
+                return _orig(tensorInput, tensorFlow, Backward_tensorGrid, Backward_tensorPartial)
+            return pwc_backward(tensorInput, tensorFlow)
+
+        bound = types.MethodType(Backward, m)
+        bound.__func__._fldr_b200_patched = True
+        object.__setattr__(m, "Backward", bound)
+        count += 1
+    return count

@@ -156,6 +156,19 @@ def test_patch_bwarp_routes_only_what_the_kernel_covers(lib):
     assert not getattr(DCTVFInet.bwarp, "_fldr_b200_patched", False)
 
 
+def test_patch_pwc_backward_patches_instances(lib):
+    from fldr_vfi_b200.integrate import patch_pwc_backward
+
+    class Decoder(torch.nn.Module):
+        def Backward(self, tensorInput, tensorFlow, g, p):
+            return "reference"
+
+    net = torch.nn.Sequential(Decoder(), torch.nn.Identity(), Decoder())
+    assert patch_pwc_backward(net) == 2 and patch_pwc_backward(net) == 0          # idempotent
+    x, fl = torch.zeros(1, 3, 4, 4), torch.zeros(1, 2, 4, 4)
+    assert net[0].Backward(x, fl, {}, {}) == "reference"                          # CPU tensors -> the reference's method
+
+
 def test_dropin_import_names_shadow_reference_modules(lib):
     """`from softSplat import Softsplat` (fLDRnet.py:22) and `from . import correlation` inside the OpticalFlow
     namespace package (PWCNet.py:4) resolve to the drop-ins when dropin/ is first on sys.path.  Importing the
