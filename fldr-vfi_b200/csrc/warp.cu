@@ -8,7 +8,7 @@
 // Coordinates follow the reference operation by operation (the __f*_rn intrinsics keep nvcc from contracting what torch
 // evaluates as separate kernels, and fuse exactly what grid_sample fuses), so the sample positions - and with them the
 // 0.999 mask decision - are bit-identical to the torch path:
-//   X = x + u;  g = 2*X / max(W-1, 1) - 1            (fLDRnet.py:562-566)
+//   X = x + u;  g = 2*X * (1/max(W-1, 1)) - 1        (fLDRnet.py:562-566; "/ scalar" as torch's CUDA kernel does it)
 //   ix = ((g + 1) * W - 1) / 2                        (grid_sample, align_corners=False default, :568)
 // i.e. ix = X*W/(W-1) - 0.5: the reference normalises for align_corners=True and samples with False; preserved.
 // Bilinear, zero padding; mask = (sum of in-frame weights >= 0.999)  (fLDRnet.py:569-574).
@@ -32,15 +32,17 @@ struct WarpTaps {
 // both: ix = ((g + 1) * size - 1) / 2   (grid_sample's align_corners=False default), rounded once
 __device__ __forceinline__ float warp_source_index(int i, float d, int size, int convention) {
     float g;
+    // "tensor / python scalar" on CUDA is a multiplication by the float32 reciprocal (torch BinaryDivTrueKernel.cu),
+    // one ulp away from the true division the CPU performs; the reference runs on the GPU, so that is what is followed
     if (convention == 0) {
-        g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)i, d)), (float)max(size - 1, 1)), 1.0f);
+        g = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, __fadd_rn((float)i, d)), __fdiv_rn(1.0f, (float)max(size - 1, 1))), 1.0f);
     } else {
         float lin = -1.0f;
         if (size > 1) {
             const float step = __fdiv_rn(2.0f, (float)(size - 1));
             lin = i < size / 2 ? __fmaf_rn(step, (float)i, -1.0f) : __fmaf_rn(-step, (float)(size - 1 - i), 1.0f);
         }
-        g = __fadd_rn(lin, __fdiv_rn(d, __fmul_rn((float)size - 1.0f, 0.5f)));
+        g = __fadd_rn(lin, __fmul_rn(d, __fdiv_rn(1.0f, __fmul_rn((float)size - 1.0f, 0.5f))));
     }
     // ((g + 1) * size - 1) / 2 with ONE rounding, as torch's grid_sample evaluates it on the CPU vector path and on
     // CUDA (size/2 and 0.5 are exact, so this fma is that expression rounded once)
@@ -140,7 +142,9 @@ __global__ void __launch_bounds__(128) bwarp_kernel(View4 src, View4 ref, View4 
     }
     if (METRIC) {
         float* op = out + (long long)n * HW + idx;
-        const float z0 = __fdiv_rn(sum[0], (float)C), z1 = __fdiv_rn(sum[1], (float)C);
+        // torch.mean on CUDA multiplies the sum by the float32 factor 1/C (ReduceMomentKernel.cu)
+        const float inv_c = __fdiv_rn(1.0f, (float)C);
+        const float z0 = __fmul_rn(sum[0], inv_c), z1 = __fmul_rn(sum[1], inv_c);
         if (vec) __stcs(reinterpret_cast<float2*>(op), make_float2(z0, z1));
         else { __stcs(op, z0); if (two) __stcs(op + 1, z1); }
     }

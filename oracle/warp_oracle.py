@@ -29,9 +29,17 @@ def _unnormalise(g, size):
     return (((g + 1.0).double() * size - 1.0) / 2.0).float()
 
 
-def _source_index(coord, size):
+def _div_scalar(t, b, cuda_semantics):
+    """``tensor / python_scalar`` as torch evaluates it: a true division on the CPU, a multiplication by the float32
+    reciprocal ``1/b`` on CUDA (BinaryDivTrueKernel.cu) - one ulp apart, and the reference runs on CUDA."""
+    if cuda_semantics:
+        return t * (torch.tensor(1.0) / torch.tensor(float(b)))
+    return t / b
+
+
+def _source_index(coord, size, cuda_semantics=False):
     """fLDRnet.py:565-566 in float32, operation by operation, followed by grid_sample's un-normalisation."""
-    g = 2.0 * coord / max(size - 1, 1) - 1.0
+    g = _div_scalar(2.0 * coord, max(size - 1, 1), cuda_semantics) - 1.0
     return _unnormalise(g, size)
 
 
@@ -47,26 +55,29 @@ def _linspace_pm1(n):
     return torch.where(torch.arange(n) < n // 2, lo, hi)
 
 
-def pwc_backward(x, flo, return_mask=False):
+def pwc_backward(x, flo, return_mask=False, cuda_semantics=False):
     """PWC-Net's Backward (OpticalFlow/PWCNet.py:116-143): grid = linspace(-1,1) per axis (:117-130), flow divided by
     (size-1)/2 (:134-135), grid_sample bilinear / zeros / align_corners=False default of the input with a ones channel
     (:136-138), mask = [ones channel > 0.999] (:140-141), output * mask (:143)."""
     x = x.float()
     flo = flo.float()
     B, C, H, W = x.shape
-    gx = _linspace_pm1(W).view(1, 1, W) + flo[:, 0] / ((W - 1.0) / 2.0)
-    gy = _linspace_pm1(H).view(1, H, 1) + flo[:, 1] / ((H - 1.0) / 2.0)
+    gx = _linspace_pm1(W).view(1, 1, W) + _div_scalar(flo[:, 0], (W - 1.0) / 2.0, cuda_semantics)
+    gy = _linspace_pm1(H).view(1, H, 1) + _div_scalar(flo[:, 1], (H - 1.0) / 2.0, cuda_semantics)
     return _sample(x, _unnormalise(gx, W), _unnormalise(gy, H), True, return_mask, strict=True)
 
 
-def bwarp(x, flo, withmask=True, return_mask=False):
+def bwarp(x, flo, withmask=True, return_mask=False, cuda_semantics=False):
+    """``cuda_semantics``: evaluate ``/ scalar`` the way torch's CUDA kernels do (see _div_scalar).  False reproduces the
+    CPU run that produced tests/golden/warp_*.npz; True is what the reference computes on a GPU and what the sm_100a
+    kernel follows."""
     x = x.float()
     flo = flo.float()
     B, C, H, W = x.shape
     xx = torch.arange(W, dtype=torch.float32).view(1, 1, W).expand(B, H, W)
     yy = torch.arange(H, dtype=torch.float32).view(1, H, 1).expand(B, H, W)
-    ix = _source_index(xx + flo[:, 0], W)
-    iy = _source_index(yy + flo[:, 1], H)
+    ix = _source_index(xx + flo[:, 0], W, cuda_semantics)
+    iy = _source_index(yy + flo[:, 1], H, cuda_semantics)
     return _sample(x, ix, iy, withmask, return_mask, strict=False)
 
 
@@ -95,7 +106,15 @@ def _sample(x, ix, iy, withmask, return_mask, strict):
     return (res, msum) if return_mask else res
 
 
-def warp_metric(x_ref, x_src, flo, alpha, withmask=True):
-    """z = mean_c(alpha * |x_ref - bwarp(x_src, flo)|), keepdim (fLDRnet.py:442-443)."""
-    w = bwarp(x_src, flo, withmask)
-    return torch.mean(float(alpha) * torch.abs(x_ref.float() - w), dim=1, keepdim=True)
+def warp_metric(x_ref, x_src, flo, alpha, withmask=True, cuda_semantics=False):
+    """z = mean_c(alpha * |x_ref - bwarp(x_src, flo)|), keepdim (fLDRnet.py:442-443).  torch.mean divides the sum by C on
+    the CPU and multiplies it by the float32 factor 1/C on CUDA (ReduceMomentKernel.cu)."""
+    w = bwarp(x_src, flo, withmask, cuda_semantics=cuda_semantics)
+    t = float(alpha) * torch.abs(x_ref.float() - w)
+    if not cuda_semantics:
+        return torch.mean(t, dim=1, keepdim=True)
+    C = t.shape[1]
+    s = t[:, 0:1]
+    for c in range(1, C):
+        s = s + t[:, c:c + 1]
+    return s * (torch.tensor(1.0) / torch.tensor(float(C)))

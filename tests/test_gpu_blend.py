@@ -1,6 +1,6 @@
 """GPU parity tests for the occlusion softmax + image synthesis row: CUDA path through the C-ABI vs
 the float64 oracle and the golden vectors of fLDRnet.py's own lines 510-524; views, t per sample, the 4K shape against the
-reference's operator sequence run in torch on the same GPU."""
+reference's own statements (lifted from baseline/_ref) run on the same GPU."""
 import pytest
 import torch
 
@@ -67,17 +67,12 @@ def test_4k_vs_reference_operator_sequence(cuda_lib):
     refine = (synth.grad((1, 6, H, W), seed=510) * 3.0).cuda()
     t_value = torch.full((1, 1, 1, 1), 0.5, device="cuda")
     T = torch.ones(1, dtype=torch.float64, device="cuda")
+    from baseline import ref_src
+    if not ref_src.available():
+        pytest.skip("baseline/_ref not staged")
     with torch.no_grad():
         got = Bl.occ_blend(refine, T, t_value, *imgs)
-        occ_all = torch.nn.functional.softmax(refine[:, 0:6] / T, dim=1)               # fLDRnet.py:511-524 restated in torch
-        tv = t_value
-        divisor = ((1 - tv) * occ_all[:, 0, :].unsqueeze(1) + tv * occ_all[:, 1, :].unsqueeze(1)
-                   + (1 - tv) * occ_all[:, 2, :].unsqueeze(1) + tv * occ_all[:, 3, :].unsqueeze(1))
-        out = (1 - tv) * occ_all[:, 0, :].unsqueeze(1) * imgs[0] + tv * occ_all[:, 1, :].unsqueeze(1) * imgs[1]
-        out += (1 - tv) * occ_all[:, 2, :].unsqueeze(1) * imgs[2] + tv * occ_all[:, 3, :].unsqueeze(1) * imgs[3]
-        out += (1 - tv) * occ_all[:, 4, :].unsqueeze(1) * imgs[4] + tv * occ_all[:, 5, :].unsqueeze(1) * imgs[5]
-        divisor += (1 - tv) * occ_all[:, 4, :].unsqueeze(1) + tv * occ_all[:, 5, :].unsqueeze(1)
-        out /= divisor
+        out, _ = ref_src.blend()(refine, T, t_value, imgs[0], imgs[1], imgs[2], imgs[3], torch.stack([imgs[4], imgs[5]], 2))
     assert out.dtype == torch.float64
     assert float((got - out).abs().max()) <= 1e-13
     # convexity: the blend of images in [-1, 1] stays in [-1, 1]

@@ -11,7 +11,10 @@ from util import load_golden
 pytestmark = pytest.mark.gpu
 
 WARP_CASES = ["warp_smooth", "warp_scatter", "warp_border", "warp_identity"]
-TOL = 2e-6        # fp32: coordinates follow the reference operation by operation, values are |x| <= 1
+TOL = 2e-6        # vs the oracle with CUDA semantics: coordinates bit for bit, what remains is the four-tap sum order
+GOLDEN_TOL = 5e-5  # vs the golden vectors: those were produced on the CPU, where "tensor / scalar" is a true division;
+                   # on CUDA (the reference's device, and what the kernel follows) it is a multiplication by the float32
+                   # reciprocal - sample positions an ulp apart, times the image gradient
 
 
 def _mod(cuda_lib):
@@ -33,11 +36,11 @@ def test_vs_golden(cuda_lib, name):
     g = load_golden(name)
     src, ref, fl, a = g["src"].cuda(), g["ref"].cuda(), g["flow"].cuda(), float(g["alpha"])
     with torch.no_grad():
-        _close(Wp.bwarp(src, fl, True), g["bwarp_mask"], name + " masked")
-        _close(Wp.bwarp(src, fl, False), g["bwarp_nomask"], name + " unmasked")
+        _close(Wp.bwarp(src, fl, True), g["bwarp_mask"], name + " masked", tol=GOLDEN_TOL)
+        _close(Wp.bwarp(src, fl, False), g["bwarp_nomask"], name + " unmasked", tol=GOLDEN_TOL)
         z = Wp.splat_metric(ref, src, fl, a)
     assert z.shape == g["metric"].shape and z.is_contiguous()
-    _close(z, g["metric"], name + " metric", tol=4e-6)
+    _close(z, g["metric"], name + " metric", tol=GOLDEN_TOL)
 
 
 @pytest.mark.parametrize("N,C,H,W,regime,scale", [(1, 3, 64, 96, "F1", 30.0), (2, 2, 33, 47, "F2", 1.0),
@@ -48,12 +51,12 @@ def test_vs_oracle_shapes(cuda_lib, N, C, H, W, regime, scale):
     x0 = synth.image(N, C, H, W, seed=5)
     x1 = synth.image(N, C, H, W, seed=6)
     fl = synth.flow(N, H, W, regime, seed=7) * scale
-    want, msum = wo.bwarp(x1, fl, True, return_mask=True)
+    want, msum = wo.bwarp(x1, fl, True, return_mask=True, cuda_semantics=True)
     with torch.no_grad():
         _close(Wp.bwarp(x1.cuda(), fl.cuda(), True), want, "masked", mask_sum=msum)
-        _close(Wp.bwarp(x1.cuda(), fl.cuda(), False), wo.bwarp(x1, fl, False), "unmasked")
-        _close(Wp.splat_metric(x0.cuda(), x1.cuda(), fl.cuda(), -1.894), wo.warp_metric(x0, x1, fl, -1.894), "metric",
-               tol=4e-6, mask_sum=msum)
+        _close(Wp.bwarp(x1.cuda(), fl.cuda(), False), wo.bwarp(x1, fl, False, cuda_semantics=True), "unmasked")
+        _close(Wp.splat_metric(x0.cuda(), x1.cuda(), fl.cuda(), -1.894),
+               wo.warp_metric(x0, x1, fl, -1.894, cuda_semantics=True), "metric", tol=4e-6, mask_sum=msum)
 
 
 @pytest.mark.parametrize("name", ["pwcwarp_smooth", "pwcwarp_scatter", "pwcwarp_border"])
@@ -62,7 +65,7 @@ def test_pwc_backward_vs_golden(cuda_lib, name):
     g = load_golden(name)
     with torch.no_grad():
         got = Wp.pwc_backward(g["input"].cuda(), g["flow"].cuda())
-    _close(got, g["out"], name, tol=1e-6 * max(1.0, float(g["out"].abs().max())))
+    _close(got, g["out"], name, tol=GOLDEN_TOL * max(1.0, float(g["out"].abs().max())))
 
 
 @pytest.mark.parametrize("N,C,H,W,scale", [(2, 32, 36, 64, 3.0), (1, 196, 9, 16, 1.0), (1, 7, 33, 47, 6.0), (2, 64, 72, 128, 10.0)])
@@ -70,7 +73,7 @@ def test_pwc_backward_vs_oracle_shapes(cuda_lib, N, C, H, W, scale):
     Wp = _mod(cuda_lib)
     x = synth.features(N, C, H, W, seed=21)
     fl = synth.flow(N, H, W, "F1", seed=22) * scale
-    want, msum = wo.pwc_backward(x, fl, return_mask=True)
+    want, msum = wo.pwc_backward(x, fl, return_mask=True, cuda_semantics=True)
     with torch.no_grad():
         got = Wp.pwc_backward(x.cuda(), fl.cuda())
     _close(got, want, "pwc backward", tol=1e-6 * max(1.0, float(want.abs().max())), mask_sum=msum)
@@ -84,7 +87,7 @@ def test_strided_views_and_nonfinite_flow(cuda_lib):
     fl = synth.flow(N, H, W, "F1", seed=9) * 20
     fl[0, 0, 3, 4] = float("nan")
     fl[1, 1, 5, 6] = float("inf")
-    want = wo.bwarp(x, fl, True)
+    want = wo.bwarp(x, fl, True, cuda_semantics=True)
     with torch.no_grad():
         got = Wp.bwarp(big.cuda()[:, ::2, :, ::2], fl.cuda(), True)
     _close(got, want, "strided")
@@ -93,7 +96,7 @@ def test_strided_views_and_nonfinite_flow(cuda_lib):
 
 def _grad_close(got, ref, what):
     err = float((got.detach().cpu().double() - ref.double()).abs().max())
-    tol = 1e-5 * max(1.0, float(ref.abs().max()))            # atomics: summation order differs from the CPU's
+    tol = 5e-5 * max(1.0, float(ref.abs().max()))            # atomics: summation order; CPU vs CUDA "/ scalar" (GOLDEN_TOL)
     assert err <= tol, f"{what}: max err {err:.3e} > {tol:.3e}"
 
 
@@ -116,7 +119,7 @@ def test_gradients_vs_oracle_autograd(cuda_lib, conv, N, C, H, W, scale):
     fl = synth.flow(N, H, W, "F1", seed=32) * scale
     go = synth.grad((N, C, H, W), seed=33)
     xo, fo = x.clone().requires_grad_(True), fl.clone().requires_grad_(True)
-    ref = wo.bwarp(xo, fo, True) if conv == 0 else wo.pwc_backward(xo, fo)
+    ref = wo.bwarp(xo, fo, True, cuda_semantics=True) if conv == 0 else wo.pwc_backward(xo, fo, cuda_semantics=True)
     gxo, gfo = torch.autograd.grad(ref, [xo, fo], go)
     xd, fd = x.cuda().requires_grad_(True), fl.cuda().requires_grad_(True)
     out = Wp.bwarp(xd, fd, True) if conv == 0 else Wp.pwc_backward(xd, fd)
@@ -143,34 +146,28 @@ def test_metric_is_forward_only_and_dtype_checked(cuda_lib):
 
 
 def test_4k_vs_torch_grid_sample_and_properties(cuda_lib):
-    """Full 2304x4096 image shape: against the torch operators the reference itself runs (fLDRnet.py:556-578) on
-    the same GPU, and through size-independent properties (the oracle would take minutes here)."""
+    """Full 2304x4096 image shape: against the reference's own bwarp method (fLDRnet.py:546-581, lifted from
+    baseline/_ref) run on the same GPU, and through size-independent properties (the oracle would take minutes here)."""
     Wp = _mod(cuda_lib)
     H, W = 2304, 4096
     x0 = synth.image(1, 3, H, W, seed=0).cuda()
     x1 = synth.image(1, 3, H, W, seed=1).cuda()
     fl = synth.flow(1, H, W, "F1", seed=2).cuda()
+    from baseline import ref_src
+    if not ref_src.available():
+        pytest.skip("baseline/_ref not staged")
+    reference_bwarp = ref_src.bwarp(x1.device, create_on_device=True)      # the reference's own method text
     with torch.no_grad():
         got = Wp.bwarp(x1, fl, True)
-        xx = torch.arange(0, W, device="cuda").view(1, 1, 1, W).expand(1, 1, H, W)
-        yy = torch.arange(0, H, device="cuda").view(1, 1, H, 1).expand(1, 1, H, W)
-        vgrid = torch.cat((xx, yy), 1).float() + fl
-        vgrid[:, 0] = 2.0 * vgrid[:, 0].clone() / max(W - 1, 1) - 1.0
-        vgrid[:, 1] = 2.0 * vgrid[:, 1].clone() / max(H - 1, 1) - 1.0
-        vgrid = vgrid.permute(0, 2, 3, 1)
-        out = torch.nn.functional.grid_sample(x1, vgrid, align_corners=False)
-        mask = torch.nn.functional.grid_sample(torch.ones_like(x1), vgrid, align_corners=False)
-        mask = mask.masked_fill_(mask < 0.999, 0).masked_fill_(mask > 0, 1)
-        want = out * mask
-        # torch's CUDA grid_sample contracts ((g+1)*W-1)/2 into an FMA: the sample position may differ by one ulp of
-        # ~2000 px (2.4e-4 px) from the unfused CPU result, times the image gradient
-        # (and a border sample whose in-frame weight sits within that ulp of the 0.999 threshold flips its mask: a
-        # handful of the 9.4 M pixels at most)
+        want = reference_bwarp(x1, fl.clone(), True)
+        # same coordinates bit for bit (the un-normalisation is rounded once on both sides); what remains is the order
+        # of the four-tap sum.  A border sample whose in-frame weight sits within rounding of the 0.999 threshold may
+        # flip its mask: allow a handful of the 9.4 M pixels
         err = (got - want).abs()
-        assert int((err > 1e-3).sum()) <= 64 and float(err.mean()) <= 2e-5, (int((err > 1e-3).sum()), float(err.mean()))
+        assert int((err > 1e-5).sum()) <= 64 and float(err.mean()) <= 1e-6, (int((err > 1e-5).sum()), float(err.mean()))
         z = Wp.splat_metric(x0, x1, fl, -1.894)
         zt = torch.mean(-1.894 * torch.abs(x0 - want), dim=1, keepdim=True)
-        assert int(((z - zt).abs() > 2e-3).sum()) <= 64
+        assert int(((z - zt).abs() > 2e-5).sum()) <= 64
         # linearity in the source, and metric(x, x, zero-residual) consistency
         got2 = Wp.bwarp(2.5 * x1, fl, True)
         assert float((got2 - 2.5 * got).abs().max()) <= 1e-5

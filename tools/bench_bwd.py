@@ -59,48 +59,16 @@ for r in rows: print(f"{r[0]:10s} {r[1]:34s} fwd {r[2]*1000:9.1f} us   fwd+bwd {
 import fldr_vfi_b200.warp as Wp
 
 
-def ref_bwarp_as_written(x, flo, device):
-    B, C, H, W = x.size()
-    xx = torch.arange(0, W).view(1, 1, 1, W).expand(B, 1, H, W)
-    yy = torch.arange(0, H).view(1, 1, H, 1).expand(B, 1, H, W)
-    grid = torch.cat((xx, yy), 1).float().to(device)
-    vgrid = grid + flo
-    vgrid[:, 0, :, :] = 2.0 * vgrid[:, 0, :, :].clone() / max(W - 1, 1) - 1.0
-    vgrid[:, 1, :, :] = 2.0 * vgrid[:, 1, :, :].clone() / max(H - 1, 1) - 1.0
-    vgrid = vgrid.permute(0, 2, 3, 1)
-    output = torch.nn.functional.grid_sample(x, vgrid, align_corners=False)
-    mask = torch.ones(x.size()).to(device)
-    mask = torch.nn.functional.grid_sample(mask, vgrid, align_corners=False)
-    mask = mask.masked_fill_(mask < 0.999, 0)
-    mask = mask.masked_fill_(mask > 0, 1)
-    return output * mask
-
-
-def ref_bwarp_device(x, flo, cache={}):
-    B, C, H, W = x.size()
-    if "g" not in cache:
-        xx = torch.arange(0, W, device=x.device).view(1, 1, 1, W).expand(B, 1, H, W)
-        yy = torch.arange(0, H, device=x.device).view(1, 1, H, 1).expand(B, 1, H, W)
-        cache["g"] = torch.cat((xx, yy), 1).float()
-        cache["ones"] = torch.ones_like(x)
-    vgrid = cache["g"] + flo
-    vgrid[:, 0, :, :] = 2.0 * vgrid[:, 0, :, :].clone() / max(W - 1, 1) - 1.0
-    vgrid[:, 1, :, :] = 2.0 * vgrid[:, 1, :, :].clone() / max(H - 1, 1) - 1.0
-    vgrid = vgrid.permute(0, 2, 3, 1)
-    output = torch.nn.functional.grid_sample(x, vgrid, align_corners=False)
-    mask = torch.nn.functional.grid_sample(cache["ones"], vgrid, align_corners=False)
-    mask = mask.masked_fill(mask < 0.999, 0)
-    mask = mask.masked_fill(mask > 0, 1)
-    return output * mask
-
+from baseline import ref_src
 
 N, Cc, H, W = 32, 3, 512, 512
 x = synth.image(N, Cc, H, W, seed=1).cuda().requires_grad_(True)
 fl = (synth.flow(N, H, W, "F1", seed=2) * 4).cuda().requires_grad_(True)
 g = synth.grad((N, Cc, H, W), seed=4).cuda()
 dev = x.device
-for name, fn in (("ours", lambda: Wp.bwarp(x, fl, True)), ("reference (as written)", lambda: ref_bwarp_as_written(x, fl, dev)),
-                 ("reference ops, device-resident grid", lambda: ref_bwarp_device(x, fl))):
+ref_as_written, ref_on_device = ref_src.bwarp(dev), ref_src.bwarp(dev, create_on_device=True)
+for name, fn in (("ours", lambda: Wp.bwarp(x, fl, True)), ("reference (as written)", lambda: ref_as_written(x, fl, True)),
+                 ("reference text, grid/ones on device", lambda: ref_on_device(x, fl, True))):
     f = timed(fn)
     fb = timed(lambda: torch.autograd.grad(fn(), [x, fl], g))
     print(f"{name:36s} bwarp 32x3x512^2   fwd {f*1000:9.1f} us   fwd+bwd {fb*1000:9.1f} us")

@@ -1,5 +1,5 @@
-"""Time the occlusion softmax + image synthesis row at the 4K shape next to the reference's operator sequence
-(fLDRnet.py:511-524) run in torch on the same GPU.    python tools/blend_probe.py"""
+"""Time the occlusion softmax + image synthesis row at the 4K shape next to the reference's own statements
+(fLDRnet.py:510-524, lifted from baseline/_ref by baseline/ref_src.py) on the same GPU.    python tools/blend_probe.py"""
 import json
 import os
 import sys
@@ -9,6 +9,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import fldr_vfi_b200.blend as Bl   # noqa: E402
+from baseline import ref_src        # noqa: E402  (the reference's own statements, from baseline/_ref)
 from oracle import synth            # noqa: E402  (input generation only)
 
 PEAK = 6549.1
@@ -16,18 +17,6 @@ try:
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
-
-
-def reference_ops(refine, T, tv, imgs):
-    occ_all = torch.nn.functional.softmax(refine[:, 0:6] / T, dim=1)
-    divisor = ((1 - tv) * occ_all[:, 0, :].unsqueeze(1) + tv * occ_all[:, 1, :].unsqueeze(1)
-               + (1 - tv) * occ_all[:, 2, :].unsqueeze(1) + tv * occ_all[:, 3, :].unsqueeze(1))
-    out = (1 - tv) * occ_all[:, 0, :].unsqueeze(1) * imgs[0] + tv * occ_all[:, 1, :].unsqueeze(1) * imgs[1]
-    out += (1 - tv) * occ_all[:, 2, :].unsqueeze(1) * imgs[2] + tv * occ_all[:, 3, :].unsqueeze(1) * imgs[3]
-    out += (1 - tv) * occ_all[:, 4, :].unsqueeze(1) * imgs[4] + tv * occ_all[:, 5, :].unsqueeze(1) * imgs[5]
-    divisor += (1 - tv) * occ_all[:, 4, :].unsqueeze(1) + tv * occ_all[:, 5, :].unsqueeze(1)
-    out /= divisor
-    return out
 
 
 def timeit(fn, reps=20):
@@ -52,9 +41,11 @@ def main():
     tv = torch.full((1, 1, 1, 1), 0.5, device="cuda")
     T = torch.ones(1, dtype=torch.float64, device="cuda")
     nbytes = H * W * (6 * 4 + 6 * C * 4 + C * 8)
+    reference_ops = ref_src.blend()
+    x_l = torch.stack([imgs[4], imgs[5]], 2)
     with torch.no_grad():
         t_o = timeit(lambda: Bl.occ_blend(refine, T, tv, *imgs))
-        t_r = timeit(lambda: reference_ops(refine, T, tv, imgs), reps=10)
+        t_r = timeit(lambda: reference_ops(refine, T, tv, imgs[0], imgs[1], imgs[2], imgs[3], x_l), reps=10)
     print(json.dumps({"op": "occ_blend C=3 (fLDRnet.py:510-524), float64", "shape": f"1x{H}x{W}", "algorithmic_MB": round(nbytes / 1e6, 1),
                       "ours_us": round(t_o, 1), "ours_GBps": round(nbytes / t_o / 1e3, 1), "frac_of_hbm_peak": round(nbytes / t_o / 1e3 / PEAK, 3),
                       "torch_reference_ops_us": round(t_r, 1), "speedup": round(t_r / t_o, 1)}), flush=True)

@@ -1,5 +1,5 @@
 """Time the backward warp / splat metric row at the 4K image shape (2304x4096, C=3) and at the flow-warp shape (C=2),
-next to the torch operator sequence the reference runs for the same thing (fLDRnet.py:546-581, 442-443) on the same GPU.
+next to the reference's own method (fLDRnet.py:546-581, lifted from baseline/_ref by baseline/ref_src.py) on the same GPU.
 
     python tools/warp_probe.py          # prints one JSON line per measurement
 """
@@ -12,6 +12,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import fldr_vfi_b200.warp as Wp   # noqa: E402
+from baseline import ref_src       # noqa: E402  (the reference's own bwarp text, from baseline/_ref)
 from oracle import synth           # noqa: E402  (input generation only)
 
 PEAK = 6549.1
@@ -19,22 +20,6 @@ try:
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
-
-
-def reference_bwarp(x, flo, withmask=True):
-    """The reference's operator sequence, restated (fLDRnet.py:546-581)."""
-    B, C, H, W = x.shape
-    xx = torch.arange(0, W, device=x.device).view(1, 1, 1, W).expand(B, 1, H, W)
-    yy = torch.arange(0, H, device=x.device).view(1, 1, H, 1).expand(B, 1, H, W)
-    vgrid = torch.cat((xx, yy), 1).float() + flo
-    vgrid[:, 0] = 2.0 * vgrid[:, 0].clone() / max(W - 1, 1) - 1.0
-    vgrid[:, 1] = 2.0 * vgrid[:, 1].clone() / max(H - 1, 1) - 1.0
-    vgrid = vgrid.permute(0, 2, 3, 1)
-    out = torch.nn.functional.grid_sample(x, vgrid, align_corners=False)
-    mask = torch.nn.functional.grid_sample(torch.ones_like(x), vgrid, align_corners=False)
-    mask = mask.masked_fill_(mask < 0.999, 0)
-    mask = mask.masked_fill_(mask > 0, 1)
-    return out * mask if withmask else out
 
 
 def timeit(fn, reps=20):
@@ -60,6 +45,10 @@ def main():
     fl2 = synth.flow(1, H, W, "F1", seed=3).cuda()
     alpha = -1.894
     px = H * W
+    # the reference's method with its grid / ones tensors allocated on the device (as written it builds them on the CPU
+    # and copies them over per call - that version is timed too, as "as_written")
+    reference_bwarp = ref_src.bwarp(x0.device, create_on_device=True)
+    as_written = ref_src.bwarp(x0.device)
     with torch.no_grad():
         rows = [
             ("bwarp C=3 (image)", 4 * px * (3 + 2 + 3), lambda: Wp.bwarp(x1, fl, True), lambda: reference_bwarp(x1, fl, True)),
@@ -72,6 +61,8 @@ def main():
             print(json.dumps({"op": what, "shape": f"1x{H}x{W}", "algorithmic_MB": round(nbytes / 1e6, 1), "ours_us": round(t_o, 1),
                               "ours_GBps": round(nbytes / t_o / 1e3, 1), "frac_of_hbm_peak": round(nbytes / t_o / 1e3 / PEAK, 3),
                               "torch_reference_ops_us": round(t_r, 1), "speedup": round(t_r / t_o, 1)}), flush=True)
+        t_w = timeit(lambda: as_written(x1, fl, True), reps=5)
+        print(json.dumps({"op": "bwarp C=3 (image), reference method as written (CPU-built grid and ones)", "us": round(t_w, 1)}), flush=True)
 
 
 if __name__ == "__main__":
