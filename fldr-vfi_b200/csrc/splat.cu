@@ -396,9 +396,14 @@ __global__ void __launch_bounds__(256) splat_normalise_kernel(const float* __res
             const float4 n4 = (qn == q) ? s4[k] : __ldcs(accn + qn * HW + pix + k);
             nrm[k] = slot == 0 ? n4.x : slot == 1 ? n4.y : slot == 2 ? n4.z : n4.w;
             d[k] = (nrm[k] == 0.f) ? 1.f : nrm[k];
-            // many-channel frames (Q > 1: the C = 48 feature splats) are instruction-bound here: one IEEE reciprocal
-            // per pixel instead of one division per channel; S * (1/norm) is within 2 ulp of the reference's S / norm
+            // one IEEE reciprocal per pixel instead of one division per channel (a float division is ~12 instructions
+            // and this pass is issue-limited as much as DRAM-limited); S * (1/norm) is within 2 ulp of the reference's
+            // S / norm, far inside the summation-order noise of the accumulation itself
+#ifndef FLDR_NORMALISE_TRUE_DIV
+            d[k] = __frcp_rn(d[k]);
+#else
             if (Q > 1) d[k] = __frcp_rn(d[k]);
+#endif
         }
         if (norm_out && q == 0) vstore<PX>(norm_out + (long long)n * HW + pix, nrm);
     }
@@ -413,7 +418,11 @@ __global__ void __launch_bounds__(256) splat_normalise_kernel(const float* __res
                 const float sv = j == 0 ? s4[k].x : j == 1 ? s4[k].y : j == 2 ? s4[k].z : s4[k].w;
                 if (g.mode == FLDR_SPLAT_RAW) yv[k] = sv;
                 else if (!has_norm) yv[k] = (sv - 0.5f) * 2.f;
+#ifndef FLDR_NORMALISE_TRUE_DIV
+                else yv[k] = (sv * d[k] - 0.5f) * 2.f;
+#else
                 else yv[k] = ((Q > 1 ? sv * d[k] : sv / d[k]) - 0.5f) * 2.f;
+#endif
             }
             vstore<PX>(op + (long long)c * HW, yv);
         }
