@@ -62,7 +62,7 @@ def worker(impl, out_path, reps, height, width):
     import torch.nn.functional as F
     from torch.autograd import Variable
     which = os.path.abspath(softSplat.__file__)
-    if impl == "ours_warp":
+    if impl in ("ours_warp", "ours_warp_keepcache"):
         # next row: replace the bwarp METHOD on the imported class - fLDRnet.py itself stays untouched
         import fLDRnet
         sys.path.insert(0, ROOT)
@@ -71,7 +71,11 @@ def worker(impl, out_path, reps, height, width):
         which += " + fldr_vfi_b200.warp.bwarp"
     model_net, device, args = R.prepare_model()
     model_net.eval()
-    if impl == "ours_warp":
+    if impl == "ours_warp_keepcache":
+        from fldr_vfi_b200.integrate import keep_allocator_cache
+        keep_allocator_cache()                 # torch.cuda.empty_cache() -> no-op (the reference calls it ~12x per forward)
+        which += " + allocator cache kept"
+    if impl in ("ours_warp", "ours_warp_keepcache"):
         from fldr_vfi_b200.integrate import patch_pwc_backward
         n_pwc = patch_pwc_backward(model_net)
         which += f" + pwc_backward on {n_pwc} decoder modules"
@@ -115,7 +119,7 @@ def worker(impl, out_path, reps, height, width):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--impl", default=None, choices=["ours", "ours_warp", "reference"])
+    ap.add_argument("--impl", default=None, choices=["ours", "ours_warp", "ours_warp_keepcache", "reference"])
     ap.add_argument("--out", default=None)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--height", type=int, default=2160)
@@ -126,7 +130,7 @@ def main():
         return
     import torch
     res = {}
-    for tag in ("reference", "reference_again", "ours", "ours_warp"):
+    for tag in ("reference", "reference_again", "ours", "ours_warp", "ours_warp_keepcache"):
         impl = "reference" if tag.startswith("reference") else tag
         out = f"/tmp/fldr_e2e_{tag}.pt"
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", impl, "--out", out, "--reps", str(a.reps),
@@ -151,6 +155,10 @@ def main():
         "with_bwarp_row": {"psnr_dB": res["ours_warp"]["psnr"], "psnr_abs_diff_dB": abs(res["ours_warp"]["psnr"] - res["reference"]["psnr"]),
                            "max_abs_output_diff": float((res["ours_warp"]["pred"] - res["reference"]["pred"]).abs().max()),
                            "e2e_speedup": med["reference"] / med["ours_warp"]},
+        "with_bwarp_row_and_allocator_cache_kept": {
+            "psnr_abs_diff_dB": abs(res["ours_warp_keepcache"]["psnr"] - res["reference"]["psnr"]),
+            "max_abs_output_diff": float((res["ours_warp_keepcache"]["pred"] - res["reference"]["pred"]).abs().max()),
+            "e2e_speedup": med["reference"] / med["ours_warp_keepcache"]},
         "softSplat_module": {k: v["softSplat"] for k, v in res.items()}}))
 
 

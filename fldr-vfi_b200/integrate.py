@@ -54,3 +54,22 @@ def patch_pwc_backward(model):
         object.__setattr__(m, "Backward", bound)
         count += 1
     return count
+
+
+def keep_allocator_cache():
+    """Make ``torch.cuda.empty_cache()`` a no-op.  The reference calls it a dozen times per forward (fLDRnet.py:465,471,
+    477,499,...) to squeeze a 4K frame into a small GPU; every call hands the caching allocator's blocks back with
+    cudaFree and the next operators cudaMalloc them again - once splat, correlation and bwarp are replaced that churn IS
+    the forward (torch.profiler: 16.9 ms of GPU work inside 35-150 ms of wall time).  On a 180 GB B200 the cache simply
+    stays.  Results are unaffected.  Returns the original function (assign it back to undo)."""
+    original = torch.cuda.empty_cache
+    if getattr(original, "_fldr_b200_patched", False):
+        return original._fldr_b200_original
+
+    def empty_cache():
+        return None
+
+    empty_cache._fldr_b200_patched = True
+    empty_cache._fldr_b200_original = original
+    torch.cuda.empty_cache = empty_cache
+    return original

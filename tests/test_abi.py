@@ -156,6 +156,16 @@ def test_patch_bwarp_routes_only_what_the_kernel_covers(lib):
     assert not getattr(DCTVFInet.bwarp, "_fldr_b200_patched", False)
 
 
+def test_keep_allocator_cache_is_reversible(lib):
+    from fldr_vfi_b200.integrate import keep_allocator_cache
+    original = keep_allocator_cache()
+    try:
+        assert keep_allocator_cache() is original and torch.cuda.empty_cache() is None
+    finally:
+        torch.cuda.empty_cache = original
+    assert not getattr(torch.cuda.empty_cache, "_fldr_b200_patched", False)
+
+
 def test_patch_pwc_backward_patches_instances(lib):
     from fldr_vfi_b200.integrate import patch_pwc_backward
 
