@@ -24,37 +24,53 @@ struct WarpTaps {
     bool keep;           // mask decision (true when masking is off)
 };
 
+// Per-axis constants of the coordinate transform, computed once on the host (IEEE float division there gives the same
+// bits as on the device; doing them per thread cost four division sequences per pixel pair).
+struct WarpAxis {
+    float inv_sm1;      // 1 / max(size-1, 1)          convention 0: "x / scalar" on CUDA is x * (1/scalar)
+    float step;         // 2 / (size-1)                convention 1: torch.linspace(-1, 1, size) step (0 when size == 1)
+    float inv_half;     // 1 / ((size-1)/2)            convention 1: flow / ((size-1)/2), same CUDA rule
+    float half_size;    // size / 2
+};
+struct WarpConsts { WarpAxis x, y; };
+
+static WarpAxis make_axis(int size) {
+    WarpAxis a;
+    a.inv_sm1 = 1.0f / (float)(size - 1 > 1 ? size - 1 : 1);
+    a.step = size > 1 ? 2.0f / (float)(size - 1) : 0.0f;
+    a.inv_half = 1.0f / (((float)size - 1.0f) * 0.5f);       // inf for size == 1, like the reference's division by zero
+    a.half_size = (float)size * 0.5f;
+    return a;
+}
+
 // convention 0 - fLDRnet.bwarp (fLDRnet.py:562-568):   g = 2*(i + d) / max(size-1, 1) - 1
 // convention 1 - PWCNet Backward (PWCNet.py:117-137):   g = linspace(-1, 1, size)[i] + d / ((size-1)/2)
 //   torch.linspace on the CPU (where the reference builds its grid, :130) is  fma(step, i, -1)  for the first half and
 //   fma(-step, size-1-i, 1)  for the second, step = 2/(size-1) in float32 - reproduced bit for bit (checked for sizes
 //   17..4096 in tests/test_oracle.py)
+// "tensor / python scalar" on CUDA is a multiplication by the float32 reciprocal (torch BinaryDivTrueKernel.cu), one ulp
+// away from the true division the CPU performs; the reference runs on the GPU, so that is what is followed.
 // both: ix = ((g + 1) * size - 1) / 2   (grid_sample's align_corners=False default), rounded once
-__device__ __forceinline__ float warp_source_index(int i, float d, int size, int convention) {
+__device__ __forceinline__ float warp_source_index(int i, float d, int size, const WarpAxis& ax, int convention) {
     float g;
-    // "tensor / python scalar" on CUDA is a multiplication by the float32 reciprocal (torch BinaryDivTrueKernel.cu),
-    // one ulp away from the true division the CPU performs; the reference runs on the GPU, so that is what is followed
     if (convention == 0) {
-        g = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, __fadd_rn((float)i, d)), __fdiv_rn(1.0f, (float)max(size - 1, 1))), 1.0f);
+        g = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, __fadd_rn((float)i, d)), ax.inv_sm1), 1.0f);
     } else {
-        float lin = -1.0f;
-        if (size > 1) {
-            const float step = __fdiv_rn(2.0f, (float)(size - 1));
-            lin = i < size / 2 ? __fmaf_rn(step, (float)i, -1.0f) : __fmaf_rn(-step, (float)(size - 1 - i), 1.0f);
-        }
-        g = __fadd_rn(lin, __fmul_rn(d, __fdiv_rn(1.0f, __fmul_rn((float)size - 1.0f, 0.5f))));
+        const float lin = size > 1 ? (i < size / 2 ? __fmaf_rn(ax.step, (float)i, -1.0f) : __fmaf_rn(-ax.step, (float)(size - 1 - i), 1.0f))
+                                   : -1.0f;
+        g = __fadd_rn(lin, __fmul_rn(d, ax.inv_half));
     }
     // ((g + 1) * size - 1) / 2 with ONE rounding, as torch's grid_sample evaluates it on the CPU vector path and on
     // CUDA (size/2 and 0.5 are exact, so this fma is that expression rounded once)
-    return __fmaf_rn(__fadd_rn(g, 1.0f), (float)size * 0.5f, -0.5f);
+    return __fmaf_rn(__fadd_rn(g, 1.0f), ax.half_size, -0.5f);
 }
 
 // sh, sw: row / pixel stride of the source plane in elements (32-bit: check_warp_args bounds the plane span)
 __device__ __forceinline__ WarpTaps warp_taps(float u, float v, int x, int y, int H, int W, int sh, int sw, bool with_mask,
-                                              int convention) {
+                                              int convention, const WarpConsts& wc) {
     WarpTaps t;
-    const float ix = warp_source_index(x, u, W, convention);
-    const float iy = warp_source_index(y, v, H, convention);
+    const float ix = warp_source_index(x, u, W, wc.x, convention);
+    const float iy = warp_source_index(y, v, H, wc.y, convention);
     const float fx0 = floorf(ix), fy0 = floorf(iy);
     const float fx1 = fx0 + 1.0f, fy1 = fy0 + 1.0f;
     // compare as floats: NaN / huge coordinates fail every test and sample nothing (torch does the same)
@@ -89,7 +105,7 @@ __device__ __forceinline__ WarpTaps warp_taps(float u, float v, int x, int y, in
 template <bool METRIC, int CU, bool EXACT>
 __global__ void __launch_bounds__(128) bwarp_kernel(View4 src, View4 ref, View4 flow, float* __restrict__ out, int C_,
                                                     int H, int W, float alpha, int with_mask, int y_base,
-                                                    int convention) {
+                                                    int convention, const __grid_constant__ WarpConsts wc) {
     const int C = EXACT ? CU : C_;
     const int x = (blockIdx.x * 128 + threadIdx.x) * 2, y = y_base + blockIdx.y, n = blockIdx.z;
     if (x >= W) return;
@@ -99,8 +115,8 @@ __global__ void __launch_bounds__(128) bwarp_kernel(View4 src, View4 ref, View4 
     const float* fq = two ? fp + flow.sw : fp;                 // odd-width tail: re-read pixel 0, result unused
     const float u0 = __ldcs(fp), v0 = __ldcs(fp + flow.sc), u1 = __ldcs(fq), v1 = __ldcs(fq + flow.sc);
     WarpTaps t[2];
-    t[0] = warp_taps(u0, v0, x, y, H, W, (int)src.sh, (int)src.sw, with_mask != 0, convention);
-    t[1] = warp_taps(u1, v1, two ? x + 1 : x, y, H, W, (int)src.sh, (int)src.sw, with_mask != 0, convention);
+    t[0] = warp_taps(u0, v0, x, y, H, W, (int)src.sh, (int)src.sw, with_mask != 0, convention, wc);
+    t[1] = warp_taps(u1, v1, two ? x + 1 : x, y, H, W, (int)src.sh, (int)src.sw, with_mask != 0, convention, wc);
     const float* sp = src.p + n * src.sn;
     const float* rp = METRIC ? ref.p + n * ref.sn + y * ref.sh + x * ref.sw : nullptr;
     const int rstep = (METRIC && two) ? (int)ref.sw : 0;
@@ -154,10 +170,11 @@ template <bool METRIC>
 static int launch_bwarp(const View4& src, const View4& ref, const View4& flow, float* out, int N, int C, int H, int W,
                         float alpha, int with_mask, int convention, cudaStream_t s) {
     const int W2 = (W + 1) / 2;
+    const WarpConsts wc = {make_axis(W), make_axis(H)};
     for (int y0 = 0; y0 < H; y0 += 65535) {          // gridDim.y limit; one launch for every frame under 65 536 rows
         const int rows = H - y0 < 65535 ? H - y0 : 65535;
         dim3 grid((unsigned)((W2 + 127) / 128), (unsigned)rows, (unsigned)N);
-#define FLDR_BWARP(CU, EXACT) bwarp_kernel<METRIC, CU, EXACT><<<grid, 128, 0, s>>>(src, ref, flow, out, C, H, W, alpha, with_mask, y0, convention)
+#define FLDR_BWARP(CU, EXACT) bwarp_kernel<METRIC, CU, EXACT><<<grid, 128, 0, s>>>(src, ref, flow, out, C, H, W, alpha, with_mask, y0, convention, wc)
         if (C == 1) FLDR_BWARP(1, true);
         else if (C == 2) FLDR_BWARP(2, true);
         else if (C == 3) FLDR_BWARP(3, true);
@@ -179,16 +196,16 @@ static int launch_bwarp(const View4& src, const View4& ref, const View4& flow, f
 // One thread per pixel, channel loop; grad_x is zero-filled by the entry point.
 __global__ void __launch_bounds__(128) bwarp_bwd_kernel(View4 src, View4 flow, View4 gout, float* __restrict__ grad_x,
                                                         float* __restrict__ grad_flow, int C, int H, int W, int with_mask,
-                                                        int y_base, int convention) {
+                                                        int y_base, int convention, const __grid_constant__ WarpConsts wc) {
     const int x = blockIdx.x * 128 + threadIdx.x, y = y_base + blockIdx.y, n = blockIdx.z;
     if (x >= W) return;
     const long long HW = (long long)H * W, idx = (long long)y * W + x;
     const float* fp = flow.p + n * flow.sn + y * flow.sh + x * flow.sw;
     const float u = __ldg(fp), v = __ldg(fp + flow.sc);
     // taps relative to a CONTIGUOUS plane for grad_x (sh = W, sw = 1) and to the source view for the x reads
-    const WarpTaps ts = warp_taps(u, v, x, y, H, W, (int)src.sh, (int)src.sw, with_mask != 0, convention);
-    const WarpTaps tg = warp_taps(u, v, x, y, H, W, W, 1, with_mask != 0, convention);
-    const float ix = warp_source_index(x, u, W, convention), iy = warp_source_index(y, v, H, convention);
+    const WarpTaps ts = warp_taps(u, v, x, y, H, W, (int)src.sh, (int)src.sw, with_mask != 0, convention, wc);
+    const WarpTaps tg = warp_taps(u, v, x, y, H, W, W, 1, with_mask != 0, convention, wc);
+    const float ix = warp_source_index(x, u, W, wc.x, convention), iy = warp_source_index(y, v, H, wc.y, convention);
     const float fx0 = floorf(ix), fy0 = floorf(iy);
     const float ax = ix - fx0, bx = (fx0 + 1.0f) - ix, ay = iy - fy0, by = (fy0 + 1.0f) - iy;
     const float* gp = gout.p + n * gout.sn + y * gout.sh + x * gout.sw;
@@ -267,10 +284,11 @@ extern "C" int fldr_bwarp_bwd(const float* x, const int64_t* x_strides, const fl
         const cudaError_t e = cudaMemsetAsync(grad_x, 0, (size_t)N * C * H * W * sizeof(float), s);
         if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
     }
+    const WarpConsts wc = {make_axis(W), make_axis(H)};
     for (int y0 = 0; y0 < H; y0 += 65535) {
         const int rows = H - y0 < 65535 ? H - y0 : 65535;
         dim3 grid((unsigned)((W + 127) / 128), (unsigned)rows, (unsigned)N);
-        bwarp_bwd_kernel<<<grid, 128, 0, s>>>(vx, vf, vg, grad_x, grad_flow, C, H, W, with_mask, y0, convention);
+        bwarp_bwd_kernel<<<grid, 128, 0, s>>>(vx, vf, vg, grad_x, grad_flow, C, H, W, with_mask, y0, convention, wc);
         const int st2 = check_launch();
         if (st2 != FLDR_OK) return st2;
     }
