@@ -2,6 +2,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace fldr {
@@ -25,18 +27,18 @@ int sm_count() {
 }  // namespace fldr
 
 namespace fldr {
-static const char* const kOptionNames[kOptCount] = {"splat_stream", "splat_ring_mb", "splat_lag", "splat_fused_max", "corr_th", "splat_pf_rows", "splat_za", "splat_l2_persist"};
-static const char* const kOptionEnv[kOptCount] = {"FLDR_SPLAT_STREAM", "FLDR_SPLAT_RING_MB", "FLDR_SPLAT_LAG", "FLDR_SPLAT_FUSED_MAX", "FLDR_CORR_TH", "FLDR_SPLAT_PF_ROWS", "FLDR_SPLAT_ZA", "FLDR_SPLAT_L2_PERSIST"};
-static const int kOptionDefault[kOptCount] = {0, 0, 0, 40000, 0, 0, 0, 0};
+static const char* const kOptionNames[kOptCount] = {"splat_stream", "splat_ring_mb", "splat_lag", "splat_fused_max", "corr_th", "splat_pf_rows"};
+static const char* const kOptionEnv[kOptCount] = {"FLDR_SPLAT_STREAM", "FLDR_SPLAT_RING_MB", "FLDR_SPLAT_LAG", "FLDR_SPLAT_FUSED_MAX", "FLDR_CORR_TH", "FLDR_SPLAT_PF_ROWS"};
+static const int kOptionDefault[kOptCount] = {1, 0, 0, 40000, 0, 0};
 static int g_options[kOptCount];
-static bool g_options_init = false;
+static std::once_flag g_options_once;
 static void init_options() {
-    if (g_options_init) return;
-    for (int i = 0; i < kOptCount; ++i) {
-        const char* e = getenv(kOptionEnv[i]);
-        g_options[i] = e ? atoi(e) : kOptionDefault[i];
-    }
-    g_options_init = true;
+    std::call_once(g_options_once, [] {
+        for (int i = 0; i < kOptCount; ++i) {
+            const char* e = getenv(kOptionEnv[i]);
+            g_options[i] = e ? atoi(e) : kOptionDefault[i];
+        }
+    });
 }
 int get_option(int opt) {
     init_options();

@@ -212,56 +212,130 @@ def test_feature_splat_L0_vs_oracle_full(cuda_lib):
     assert_splat_close(gi, gio, "feature L0 grad_input")
 
 
+def _raw_call(lib, x, fl, z, mode=3):
+    """fldr_splat_fwd through the C ABI with a workspace the test owns; returns (out, path, reach rows, flag word)."""
+    import ctypes
+    import fldr_vfi_b200._lib as L
+    N, C, H, W = x.shape
+    info = (ctypes.c_int64 * 8)()
+    assert lib.fldr_splat_fwd_plan(mode, N, C, H, W, int(z is not None), info) == 0
+    ws = torch.zeros(int(info[6]), dtype=torch.uint8, device="cuda")
+    out = torch.empty_like(x)
+    st = lib.fldr_splat_fwd(mode, L.ptr(x), L.strides(x), L.ptr(fl), L.strides(fl), L.ptr(z), None if z is None else L.strides(z),
+                            L.ptr(out), None, N, C, H, W, L.ptr(ws), int(info[6]),
+                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    L.check(st)
+    torch.cuda.synchronize()
+    flag = int(ws[int(info[3]):int(info[3]) + 4].view(torch.int32)[0]) if info[0] == 2 else -1
+    return out, int(info[0]), int(info[1]), flag
+
+
 @pytest.fixture
-def streaming(cuda_lib):
-    """Opt into the single-launch streaming kernel for one test."""
-    cuda_lib.fldr_set_option(b"splat_stream", 1)
+def ring_everywhere(cuda_lib):
+    """Send small frames through the streaming kernel too (they normally take the single cooperative launch)."""
+    old = cuda_lib.fldr_get_option(b"splat_fused_max")
+    cuda_lib.fldr_set_option(b"splat_fused_max", 0)
     yield
+    cuda_lib.fldr_set_option(b"splat_fused_max", old)
+
+
+@pytest.fixture
+def whole_frame(cuda_lib):
+    """Switch the streaming kernel off: the whole-frame three-pass path serves the call."""
     cuda_lib.fldr_set_option(b"splat_stream", 0)
+    yield
+    cuda_lib.fldr_set_option(b"splat_stream", 1)
 
 
 @pytest.mark.parametrize("shape,regime,with_metric", [
-    ((1, 3, 256, 448), "F1", True), ((1, 48, 32, 56), "F2", False), ((2, 5, 33, 47), "FB", True), ((3, 7, 5, 130), "F2", False),
+    ((1, 3, 256, 448), "F1", True), ((1, 48, 32, 56), "F2", False), ((2, 5, 36, 48), "FB", False), ((3, 7, 8, 132), "F2", False),
+    ((2, 3, 64, 96), "F3", True), ((1, 3, 4, 4), "F0", True), ((2, 3, 40, 260), "FB", True),
 ])
-def test_streaming_kernel_small_frames(cuda_lib, streaming, shape, regime, with_metric):
-    S = _mods(cuda_lib)
+def test_ring_kernel_small_frames(cuda_lib, ring_everywhere, shape, regime, with_metric):
+    """Every quad shape / metric kind / ragged tile of the streaming kernel against the oracle; the ring holds the whole
+    batch here, so nothing may raise the flag word."""
     N, C, H, W = shape
     x = synth.features(N, C, H, W, seed=11)
     fl = synth.flow(N, H, W, regime, seed=12)
     z = synth.metric(N, H, W, seed=13) if with_metric else None
-    y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), None if z is None else z.cuda(), "softmax")
-    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "streaming small", mag=1.0)
+    y, path, reach, flag = _raw_call(cuda_lib, x.cuda(), fl.cuda(), None if z is None else z.cuda())
+    assert path == 2 and reach == -1 and flag == 0
+    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "ring small", mag=1.0)
 
 
-def test_streaming_kernel_4k(cuda_lib, streaming):
+@pytest.mark.parametrize("mode", ["summation", "average", "linear", "raw"])
+def test_ring_kernel_other_modes(cuda_lib, ring_everywhere, mode):
+    import fldr_vfi_b200._lib as L
+    N, C, H, W = 2, 6 if mode != "linear" else 3, 40, 64
+    x = synth.features(N, C, H, W, seed=21)
+    fl = synth.flow(N, H, W, "F2", seed=22)
+    z = synth.metric(N, H, W, seed=23) if mode == "linear" else None
+    ref = so.splat_raw(x, fl) if mode == "raw" else so.function_softsplat(x, fl, z, mode)
+    y, path, _, flag = _raw_call(cuda_lib, x.cuda(), fl.cuda(), None if z is None else z.cuda(), L.SPLAT_MODES[mode])
+    assert path == 2 and flag == 0
+    assert_splat_close(y, ref, "ring " + mode)
+
+
+def test_whole_frame_path_4k(cuda_lib, whole_frame):
+    """The three-pass path (what the fallback and unaligned views run) at the 4K size."""
     S = _mods(cuda_lib)
     x = synth.image(1, 3, H4K, W4K, seed=56)
     fl = synth.flow(1, H4K, W4K, "F1", seed=57)
     z = synth.metric(1, H4K, W4K, seed=58)
     y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), z.cuda(), "softmax")
-    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "4K streaming", mag=1.0)
+    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "4K whole-frame", mag=1.0)
 
 
-def test_bounded_ring_overflow_falls_back(cuda_lib, streaming):
-    """Frames taller than the L2-resident ring bound the vertical reach of the streaming kernel; a flow beyond it must
-    flag the overflow on the device and re-do the call with the whole-frame path (no host sync) - same result."""
+def test_ring_kernel_4k_stays_on_ring(cuda_lib):
+    """The headline flow regimes F1 / F2 fit the 4K ring's vertical reach: the flag word stays 0 (no fallback ran)."""
+    x = synth.image(1, 3, H4K, W4K, seed=56).cuda()
+    z = synth.metric(1, H4K, W4K, seed=58).cuda()
+    for regime, seed in (("F1", 57), ("F2", 59)):
+        fl = synth.flow(1, H4K, W4K, regime, seed=seed)
+        y, path, reach, flag = _raw_call(cuda_lib, x, fl.cuda(), z)
+        assert path == 2 and reach >= 64 and flag == 0, (regime, path, reach, flag)
+        assert float(fl[:, 1].abs().max()) < reach
+
+
+def test_unaligned_views_take_whole_frame_path(cuda_lib):
+    """Views the bulk copies cannot take (odd width, column-sliced rows) are served by the whole-frame path."""
     S = _mods(cuda_lib)
-    H, W = 1152, 4096                      # ring for W=4096 holds 512 rows -> reach ~88 rows
+    N, H, W = 1, 300, 1027
+    x = synth.image(N, 3, H, W, seed=61)
+    fl = synth.flow(N, H, W, "F1", seed=62)
+    z = synth.metric(N, H, W, seed=63)
+    y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), z.cuda(), "softmax")
+    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "odd width", mag=1.0)
+    xs = x.cuda()[:, :, :, 3:1027]          # W = 1024 but rows start 12 bytes into a line
+    fs, zs = fl.cuda()[:, :, :, 3:1027], z.cuda()[:, :, :, 3:1027]
+    y = S.FunctionSoftsplat(xs, fs, zs, "softmax")
+    assert_splat_close(y, so.function_softsplat(x[:, :, :, 3:1027], fl[:, :, :, 3:1027], z[:, :, :, 3:1027], "softmax"), "sliced rows", mag=1.0)
+
+
+def test_bounded_ring_overflow_falls_back(cuda_lib):
+    """Frames taller than the L2-resident ring bound the vertical reach of the streaming kernel; a flow beyond it must
+    raise the flag on the device and the guarded whole-frame launches re-do the call (no host sync) - same result."""
+    S = _mods(cuda_lib)
+    H, W = 1152, 4096                      # ring for W=4096 holds 512 rows
     x = synth.image(1, 3, H, W, seed=81)
     z = synth.metric(1, H, W, seed=82)
     fl = synth.flow(1, H, W, "F1", seed=83)
     fl[:, 1, 300:340, 1000:1400] += 260.0      # a block moving 260 rows down: beyond the reach
     fl[:, 1, 900:930, 2000:2100] -= 400.0      # and one moving 400 rows up
-    y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), z.cuda(), "softmax")
-    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "overflow fallback", mag=1.0)
+    ref = so.function_softsplat(x, fl, z, "softmax")
+    y, path, reach, flag = _raw_call(cuda_lib, x.cuda(), fl.cuda(), z.cuda())
+    assert path == 2 and 0 < reach < 260 and flag == 1
+    assert_splat_close(y, ref, "overflow fallback", mag=1.0)
+    assert_splat_close(S.FunctionSoftsplat(x.cuda(), fl.cuda(), z.cuda(), "softmax"), ref, "overflow fallback (wrapper)", mag=1.0)
     # and the in-reach case on the same shape (pure streaming path) for contrast
     fl2 = synth.flow(1, H, W, "F1", seed=84)
-    fl2[:, 1, 300:340, 1000:1400] += 150.0
-    y2 = S.FunctionSoftsplat(x.cuda(), fl2.cuda(), z.cuda(), "softmax")
+    fl2[:, 1, 300:340, 1000:1400] += 60.0
+    y2, _, _, flag2 = _raw_call(cuda_lib, x.cuda(), fl2.cuda(), z.cuda())
+    assert flag2 == 0
     assert_splat_close(y2, so.function_softsplat(x, fl2, z, "softmax"), "in-reach streaming", mag=1.0)
 
 
-def test_batched_tall_frames_stream(cuda_lib, streaming):
+def test_batched_tall_frames_ring(cuda_lib):
     """N > 1 with a ring smaller than the batch: strips of consecutive samples share ring slots across epochs."""
     S = _mods(cuda_lib)
     N, H, W = 3, 640, 4096
@@ -279,44 +353,34 @@ def test_batched_tall_frames_stream(cuda_lib, streaming):
     assert_splat_close(grads[0], gi, "batched tall grad_input", cond=gi - gi64)
     assert_splat_close(grads[1], gf, "batched tall grad_flow", cond=gf - gf64)
     assert_splat_close(grads[2], gz, "batched tall grad_metric", cond=gz - gz64)
+    _, path, _, flag = _raw_call(cuda_lib, x.cuda(), fl.cuda(), z.cuda())
+    assert path == 2 and flag == 0
 
 
-@pytest.fixture
-def zero_ahead(cuda_lib):
-    """Opt into the zero-ahead scatter for one test."""
-    cuda_lib.fldr_set_option(b"splat_za", 8)
-    yield
-    cuda_lib.fldr_set_option(b"splat_za", 0)
-
-
-def test_zero_ahead_scatter_overflow_falls_back(cuda_lib, zero_ahead):
-    """Opt-in path for DRAM-resident accumulators: the scatter kernel zeroes the accumulator a bounded distance ahead
-    of itself; a flow beyond that reach must flag the overflow on the device and re-do the call with the plain
-    whole-frame path (no host sync) - same result.  Also the in-reach case and zero-ahead switched off, for contrast."""
+def test_cfg5_training_shapes_vs_oracle(cuda_lib):
+    """BASELINE configs[4] at its literal shapes: 32 x 3 x 512 x 512 image splat with all three gradients and the
+    32 x 48 x 64 x 64 feature splat with grad_input (flow detached, fLDRnet.py:384)."""
     S = _mods(cuda_lib)
-    H, W = 1152, 4096
-    x = synth.image(1, 3, H, W, seed=81)
-    z = synth.metric(1, H, W, seed=82)
-    fl = synth.flow(1, H, W, "F1", seed=83)
-    fl[:, 1, 300:340, 1000:1400] += 260.0      # 260 rows down: beyond the +-128-row reach
-    fl[:, 1, 900:930, 2000:2100] -= 400.0      # 400 rows up
-    ref = so.function_softsplat(x, fl, z, "softmax")
-    y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), z.cuda(), "softmax")
-    assert_splat_close(y, ref, "zero-ahead overflow fallback", mag=1.0)
-    fl2 = synth.flow(1, H, W, "F1", seed=84)
-    fl2[:, 1, 300:340, 1000:1400] += 100.0
-    ref2 = so.function_softsplat(x, fl2, z, "softmax")
-    assert_splat_close(S.FunctionSoftsplat(x.cuda(), fl2.cuda(), z.cuda(), "softmax"), ref2, "zero-ahead in reach", mag=1.0)
-    cuda_lib.fldr_set_option(b"splat_za", 16)
-    assert_splat_close(S.FunctionSoftsplat(x.cuda(), fl2.cuda(), z.cuda(), "softmax"), ref2, "zero-ahead 16-row strips", mag=1.0)
-
-
-def test_zero_ahead_batched_multi_quad(cuda_lib, zero_ahead):
-    """Zero-ahead across plane boundaries: N = 2 samples x 2 channel quads (C = 6 + weight), tall frames."""
-    S = _mods(cuda_lib)
-    N, C, H, W = 2, 6, 640, 2048
-    x = synth.features(N, C, H, W, seed=95)
-    fl = synth.flow(N, H, W, "F1", seed=96) * 2
-    z = synth.metric(N, H, W, seed=97)
-    y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), z.cuda(), "softmax")
-    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "zero-ahead batched multi-quad", mag=1.0)
+    N, H, W = 32, 512, 512
+    x = synth.image(N, 3, H, W, seed=101)
+    z = synth.metric(N, H, W, seed=102)
+    fl = synth.flow(N, H, W, "F1", seed=103) * 4
+    g = synth.grad((N, 3, H, W), seed=104)
+    xd, fd, zd = x.cuda().requires_grad_(True), fl.cuda().requires_grad_(True), z.cuda().requires_grad_(True)
+    y = S.FunctionSoftsplat(xd, fd, zd, "softmax")
+    grads = torch.autograd.grad(y, [xd, fd, zd], g.cuda())
+    yo, gi, gf, gz = so.function_softsplat_grads(x, fl, z, "softmax", g)
+    _, gi64, gf64, gz64 = so.function_softsplat_grads(x.double(), fl.double(), z.double(), "softmax", g.double())
+    assert_splat_close(y, yo, "cfg5 image out", mag=1.0)
+    assert_splat_close(grads[0], gi, "cfg5 image grad_input", cond=gi - gi64)
+    assert_splat_close(grads[1], gf, "cfg5 image grad_flow", cond=gf - gf64)
+    assert_splat_close(grads[2], gz, "cfg5 image grad_metric", cond=gz - gz64)
+    xf = synth.features(N, 48, 64, 64, seed=105)
+    ff = synth.flow(N, 64, 64, "F1", seed=106) * 16
+    gf_ = synth.grad((N, 48, 64, 64), seed=107)
+    xfd = xf.cuda().requires_grad_(True)
+    yf = S.Softsplat()(xfd, ff.cuda())
+    (gif,) = torch.autograd.grad(yf, [xfd], gf_.cuda())
+    yfo, gifo, _, _ = so.function_softsplat_grads(xf, ff, None, "softmax", gf_)
+    assert_splat_close(yf, yfo, "cfg5 feature out")
+    assert_splat_close(gif, gifo, "cfg5 feature grad_input")
