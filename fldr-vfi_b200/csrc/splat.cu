@@ -529,7 +529,10 @@ static int plan_fwd(int mode, int N, int C, int H, int W, bool has_metric, FwdPl
     while (cap_rows * 2 * row_bytes <= ((size_t)kRingMbMax << 20)) cap_rows *= 2;
     if (rows * row_bytes > ((size_t)kRingMbMax << 20) && rows > cap_rows) rows = cap_rows;
     p.ring_bytes = align_up(rows * row_bytes, 256);
-    p.ctrl_bytes = align_up(((size_t)kRingCtrlCounters + (size_t)N * ((H + 7) / 8) + rows / 8) * 4, 256);
+    p.ctrl_bytes = align_up(((size_t)kRingCtrlCounters + 2 * (size_t)N * ((H + 7) / 8) + rows / 8) * 4, 256);
+#ifdef FLDR_RING_TRACE
+    p.ctrl_bytes += 8 * 128 * 8 * 8 + 256;
+#endif
     if (p.ring.ok && (p.ring.ring_bytes > p.ring_bytes || p.ring.ctrl_bytes > p.ctrl_bytes)) p.ring.ok = false;
     p.total_bytes = p.ring_bytes + p.ctrl_bytes + p.full_bytes;
     return FLDR_OK;
@@ -691,7 +694,9 @@ extern "C" int fldr_splat_fwd(int mode, const float* in, const int64_t* in_strid
 
     if (pick_path(p, vin, vfl, vme, out, norm) != 2) return launch_whole_frame(p, vin, vfl, vme, full, out, norm, nullptr, s);
 
-    if ((st = launch_ring(p.ring, p.g, vin, vfl, vme, ring, ctrl, out, norm, s)) != FLDR_OK) return st;
+    st = launch_ring(p.ring, p.g, vin, vfl, vme, ring, ctrl, out, norm, s);
+    if (st == FLDR_ERR_UNSUPPORTED) return launch_whole_frame(p, vin, vfl, vme, full, out, norm, nullptr, s);   // no tensor map for these views
+    if (st != FLDR_OK) return st;
     // bounded reach: arm the whole-frame path; its launches exit at once unless the ring kernel raised the flag
     if (p.ring.rg.bounded) return launch_whole_frame(p, vin, vfl, vme, full, out, norm, ctrl + kRingCtrlFlag, s);
     return FLDR_OK;

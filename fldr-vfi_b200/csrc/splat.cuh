@@ -41,13 +41,12 @@ struct RingGeom {
     int Q;           // channel quads
     int RS;          // ring strips
     int Ds;          // vertical reach in strips
-    int D2;          // Ds + lag: N(J) is handed out with S(J + D2)
     int pitch;       // ring row pitch in float4 cells = W + 2 (one guard cell either side: no x test on the reductions)
     int ring_rows;   // RS * 8
     int mask;        // ring_rows - 1 (bounded: a power of two) or all ones (the ring holds the whole batch: no wrap)
-    int nZ;          // leading zero-fill items
-    int TQ, GI;      // T * Q scatter items + T normalise items per group
-    int total;       // all tickets
+    int nZs, nZ;     // ring slots zeroed up front = min(RS, NT), and the zero-fill items that takes (nZs * T)
+    int TQ;          // T * Q scatter items per strip (T normalise items per strip)
+    int total;       // all work items
     int bounded;     // ring smaller than the batch: reach is bounded, the whole-frame fallback must be armed
     int spin_limit;  // watchdog of the dependency polls
 };
@@ -58,9 +57,9 @@ struct RingPlan {
     size_t ring_bytes, ctrl_bytes;
 };
 
-constexpr int kRingCtrlTicket = 0;     // ctrl word indices (unsigned)
+constexpr int kRingCtrlClaim = 0;      // ctrl word indices (unsigned): {N tickets claimed, S tickets claimed, scatter frontier, clean frontier}
 constexpr int kRingCtrlFlag = 32;      // bit 0: a source left the ring's reach, bit 1: watchdog
-constexpr int kRingCtrlCounters = 64;  // sdone[NT], then clean[RS]
+constexpr int kRingCtrlCounters = 64;  // sdone[NT], then ev[nZs + NT]
 
 // Can the ring kernel serve this call?  (layout / alignment requirements of its bulk copies and vector stores)
 bool ring_eligible(const SplatGeom& g, const View4& in, const View4& flow, const View4& metric, const float* out, const float* norm);

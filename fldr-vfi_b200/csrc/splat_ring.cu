@@ -24,7 +24,7 @@
 //               the guarded whole-frame launches that follow re-do the call (no host sync).  When the ring holds every
 //               strip of the batch the reach is unbounded.
 //
-// CTA = 4 consumer warps + 3 helper warps (warp-specialised, mbarrier pipeline):
+// CTA = 4 consumer warps + 2 helper warps (warp-specialised, mbarrier pipeline):
 //   producer    draws tickets, decodes them, and stages the inputs of S items in shared memory with cp.async.bulk
 //               (one 512-byte row segment per copy, L2 evict-first) - up to NST items ahead of the consumers, so the
 //               serial row walk below never waits for DRAM;
@@ -50,12 +50,19 @@ namespace ring {
 constexpr int R = 8;                          // rows per strip
 constexpr int TW = 128;                       // columns per tile = consumer threads
 constexpr int NST = 2;                        // staged S inputs per CTA
-constexpr int NSLOT = 4;                      // item descriptors in flight per CTA (>= NST)
+#ifndef FLDR_RING_NSLOT
+#define FLDR_RING_NSLOT 4
+#endif
+constexpr int NSLOT = FLDR_RING_NSLOT;        // item descriptors in flight per CTA (>= NST)
 constexpr int PLANES = 6;                     // staged planes per S item: flow 2 + metric 0/1 + channels of the quad
 constexpr int STAGE_FLOATS = PLANES * R * TW; // 24 KiB
 constexpr int kConsumerWarps = 4;
-constexpr int kProducerWarp = 4, kGateWarp = 5, kSignalWarp = 6;
-constexpr int kThreads = (kConsumerWarps + 3) * 32;
+constexpr int kProducerWarp = 4, kSignalWarp = 5;
+constexpr int kThreads = (kConsumerWarps + 2) * 32;
+#ifndef FLDR_RING_CTAS
+#define FLDR_RING_CTAS 4
+#endif
+constexpr int kCtasPerSm = FLDR_RING_CTAS;    // resident CTAs per SM the kernel is compiled for (register cap)
 constexpr int kSent = -(1 << 30);             // "no cell": stays negative after + 1
 enum Kind { kExit = 0, kZero = 1, kScatter = 2, kNorm = 3 };
 
@@ -80,6 +87,50 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_relaxed_v4(const unsigned* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// strips whose dependency window [J - Ds, min(J + Ds, end of J's sample)] lies below the frontier f (a count of leading
+// complete strips / clean events): monotone in f, so tickets below it are claimable in order
+__device__ __forceinline__ int frontier_limit(int f, const RingGeom& rg) {
+    const int a = f - rg.Ds, b = (f / rg.NS) * rg.NS;
+    const int m = a > b ? a : b;
+    return m < 0 ? 0 : (m > rg.NT ? rg.NT : m);
+}
+// Advance the two frontiers (leading complete strips of the scatter counters / leading complete clean events) from the
+// per-strip counters.  Warp-wide; any warp may call it at any time: a frontier only moves forward (atomicMax).
+__device__ __forceinline__ bool advance_frontiers(unsigned* __restrict__ ctrl, const unsigned* __restrict__ sdone,
+                                                  const unsigned* __restrict__ ev, const RingGeom& rg, int sf, int cf, int lane) {
+    int f = sf;
+    while (f < rg.NT) {
+        const unsigned v = (f + lane < rg.NT) ? ld_relaxed_u32(&sdone[f + lane]) : 0u;
+        const unsigned m = __ballot_sync(0xffffffffu, v >= (unsigned)rg.TQ);
+        const int cnt = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
+        f += cnt;
+        if (cnt < 32) break;
+    }
+    const int nev = rg.nZs + rg.NT;
+    int e = cf;
+    while (e < nev) {
+        const unsigned v = (e + lane < nev) ? ld_relaxed_u32(&ev[e + lane]) : 0u;
+        const unsigned m = __ballot_sync(0xffffffffu, v >= (unsigned)rg.T);
+        const int cnt = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
+        e += cnt;
+        if (cnt < 32) break;
+    }
+    if (lane == 0) {
+        if (f > sf) atomicMax(&ctrl[kRingCtrlClaim + 2], (unsigned)f);
+        if (e > cf) atomicMax(&ctrl[kRingCtrlClaim + 3], (unsigned)e);
+    }
+    return f > sf || e > cf;
+}
 __device__ __forceinline__ void red_add_u32(unsigned* p, unsigned v) {
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -90,6 +141,11 @@ __device__ __forceinline__ float4 ld_cg4(const float4* p) {
 }
 __device__ __forceinline__ void st_cg4_zero(float4* p) {
     asm volatile("st.global.cg.v4.f32 [%0], {%1, %1, %1, %1};" ::"l"(p), "f"(0.f) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load_plain(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -110,6 +166,14 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
         ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+// one [planes][8 rows][128 columns] box of an NCHW input, global -> shared; rows / columns / channels outside the tensor are
+// zero-filled by the TMA unit.  The inputs are read exactly once: evict-first in L2.
+__device__ __forceinline__ void tma_box_load(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int c, int n, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(c), "r"(n), "l"(pol)
         : "memory");
 }
 // cell `off` of plane `base` += v, only when off >= 0 (one predicated REDG, no branch)
@@ -280,8 +344,66 @@ __device__ __forceinline__ void ring_normalise_item(const ring::ItemDesc& d, con
     }
 }
 
+// N item of a single-quad splat (the image splats): the gatekeeper has copied the strip's ring cells into the stage
+// ([8 rows][128 cells] float4) once the dependencies were satisfied, so nothing here waits for L2.  A lane owns the cells
+// lane, lane+32, lane+64, lane+96 of a row (conflict-free LDS.128, full-line stores).
+__device__ __forceinline__ void ring_normalise_item_staged(const float4* __restrict__ st4, const ring::ItemDesc& d,
+                                                           const SplatGeom& g, const RingGeom& rg, float4* __restrict__ ringbuf,
+                                                           float* __restrict__ out, float* __restrict__ norm_out, int warp, int lane) {
+    using namespace ring;
+    const long long HW = (long long)g.H * g.W;
+    const bool has_norm = g.CA > g.C, raw = g.mode == FLDR_SPLAT_RAW;
+    const int slot = g.C & 3;                       // has_norm: the normaliser's lane inside the quad (C <= 3)
+    for (int r = warp; r < d.rows; r += kConsumerWarps) {
+        const int y = d.yb + r;
+        float4* cp = ringbuf + (size_t)((d.row0 + y) & rg.mask) * rg.pitch + 1 + d.x0;
+        float* op = out + (long long)d.n * g.C * HW + (long long)y * g.W + d.x0;
+        float* np = norm_out ? norm_out + (long long)d.n * HW + (long long)y * g.W + d.x0 : nullptr;
+        float4 s4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s4[k] = st4[r * TW + lane + 32 * k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xl = lane + 32 * k;
+            if (xl < d.cols) {
+                st_cg4_zero(cp + xl);
+                float dv = 1.f;
+                if (has_norm) {
+                    const float nrm = slot == 0 ? s4[k].x : slot == 1 ? s4[k].y : slot == 2 ? s4[k].z : s4[k].w;
+                    dv = norm_recip(nrm);
+                    if (np) __stcs(np + xl, nrm);
+                }
+                const float sv[4] = {s4[k].x, s4[k].y, s4[k].z, s4[k].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < g.C) __stcs(op + (long long)j * HW + xl, post_scale(sv[j], dv, raw, has_norm));
+            }
+        }
+    }
+}
+
+#ifdef FLDR_RING_TRACE
+// per-item event times (SM clock) of the first 8 CTAs: trace[blk][item][8] behind the counters (plan_ring reserves the space)
+#define TRACE(ev_, val_) do { if (blockIdx.x < 8 && k < 128 && lane == 0) trace[((size_t)blockIdx.x * 128 + k) * 8 + (ev_)] = (val_); } while (0)
+#define TRACE_T(ev_) TRACE(ev_, (unsigned long long)clock64())
+#else
+#define TRACE(ev_, val_) do {} while (0)
+#define TRACE_T(ev_) do {} while (0)
+#endif
+#ifdef FLDR_RING_STATS
+#define STAT_T0() const long long _t0 = clock64()
+#define STAT_ADD(i) do { if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(ctrl + 40) + (i), (unsigned long long)(clock64() - _t0)); } while (0)
+#define STAT_INC(i, v) do { if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(ctrl + 40) + (i), (unsigned long long)(v)); } while (0)
+#else
+#define STAT_T0() do {} while (0)
+#define STAT_ADD(i) do {} while (0)
+#define STAT_INC(i, v) do {} while (0)
+#endif
+
 template <int WKIND, bool PRE, int QS, bool BOUNDED>
-__global__ void __launch_bounds__(ring::kThreads, 3) splat_ring_kernel(View4 in, View4 flow, View4 metric,
+__global__ void __launch_bounds__(ring::kThreads, ring::kCtasPerSm) splat_ring_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                                       const __grid_constant__ CUtensorMap tm_flow,
+                                                                       const __grid_constant__ CUtensorMap tm_metric,
                                                                        float4* __restrict__ ringbuf, unsigned* __restrict__ ctrl,
                                                                        float* __restrict__ out, float* __restrict__ norm_out,
                                                                        SplatGeom g, RingGeom rg) {
@@ -299,7 +421,7 @@ __global__ void __launch_bounds__(ring::kThreads, 3) splat_ring_kernel(View4 in,
     if (tid == 0) {
         for (int i = 0; i < NSLOT; ++i) {
             mbar_init(&bar_posted[i], 1);
-            mbar_init(&bar_full[i], 2);            // producer (after issuing the copies) + gatekeeper
+            mbar_init(&bar_full[i], 1);            // producer, after issuing the copies (+ their bytes)
             mbar_init(&bar_done[i], kConsumerWarps);
             mbar_init(&bar_free[i], 1);
             s_ovf[i] = 0;
@@ -308,34 +430,73 @@ __global__ void __launch_bounds__(ring::kThreads, 3) splat_ring_kernel(View4 in,
     }
     __syncthreads();
 
-    unsigned* sdone = ctrl + kRingCtrlCounters;
-    unsigned* clean = sdone + rg.NT;
+    unsigned* sdone = ctrl + kRingCtrlCounters;      // [NT] scatter tiles (x quads) done per strip
+    unsigned* ev = sdone + rg.NT;                    // [nZs + NT] clean events: Z(slot) then N(strip); strip JJ's ring slot was last
+                                                     // cleaned by event JJ (Z(JJ) for the first tenants, N(JJ - RS) afterwards)
     unsigned* flag = ctrl + kRingCtrlFlag;
+#ifdef FLDR_RING_TRACE
+    unsigned long long* trace = reinterpret_cast<unsigned long long*>(ev + rg.nZs + rg.NT + ((rg.NT + rg.nZs + rg.NT) & 1));
+#endif
 
     if (warp == kProducerWarp) {
         // ------------------------------------------------------------------ producer: tickets, descriptors, input staging
         const uint64_t pol = policy_evict_first();
-        unsigned t_raw = (lane == 0) ? atomicAdd(&ctrl[kRingCtrlTicket], 1u) : 0u;
-        for (int k = 0;;) {
-            const int idx = (int)__shfl_sync(0xffffffffu, t_raw, 0);
+        const int n_total = rg.nZ + rg.NT * rg.T, s_total = rg.NT * rg.TQ;
+        // Work is assigned statically: CTA b owns the scatter tickets b, b + G, ... and the zero / normalise tickets
+        // b, b + G, ... (G = grid size), and takes them in order - no ticket atomics.  A ticket is only started once the
+        // frontiers (read with one relaxed load, cached) cover its dependencies, so a CTA never holds an item that waits
+        // for work another CTA has not started; zero / normalise tickets go first (they free ring rows).
+        int next_n = blockIdx.x, next_s = blockIdx.x;
+        int sf = 0, cf = 0;
+        if (lane == 0) { tma_prefetch_desc(&tm_in); tma_prefetch_desc(&tm_flow); if (g.has_metric) tma_prefetch_desc(&tm_metric); }
+        for (int k = 0;; ++k) {
+            const int slot = k % NSLOT, use = k / NSLOT;
+            { STAT_T0(); if (k >= NSLOT) mbar_wait_wd(&bar_free[slot], (use - 1) & 1); STAT_ADD(6); }
+            TRACE_T(0);
             ItemDesc d;
             d.kind = kExit; d.J = 0; d.n = 0; d.q = 0; d.x0 = 0; d.cols = 0; d.yb = 0; d.rows = 0; d.row0 = 0;
             d.dep_lo = 0; d.dep_hi = -1; d.ylo = 0.f; d.yhi = 0.f;
-            bool exists = true;
             int t = 0;
-            if (idx < rg.total) {
-                if (idx < rg.nZ) { d.kind = kZero; d.J = idx / rg.T; t = idx % rg.T; }
-                else {
-                    const int k2 = idx - rg.nZ;
-                    const int grp = k2 / rg.GI, r = k2 % rg.GI;
-                    if (r < rg.TQ) { d.kind = kScatter; d.J = grp; d.q = r / rg.T; t = r % rg.T; exists = grp < rg.NT; }
-                    else { d.kind = kNorm; d.J = grp - rg.D2; t = r - rg.TQ; exists = d.J >= 0 && d.J < rg.NT; }
+            {
+                STAT_T0();
+                int spins = 0;
+                for (;;) {
+                    if (next_n < n_total) {
+                        const int J = next_n < rg.nZ ? -1 : (next_n - rg.nZ) / rg.T;
+                        if (J < frontier_limit(sf, rg)) {
+                            if (J < 0) { d.kind = kZero; d.J = next_n / rg.T; t = next_n % rg.T; }
+                            else { d.kind = kNorm; d.J = J; t = (next_n - rg.nZ) % rg.T; }
+                            next_n += gridDim.x;
+                            break;
+                        }
+                    }
+                    if (next_s < s_total) {
+                        const int J = next_s / rg.TQ;
+                        if (J < frontier_limit(cf, rg)) {
+                            d.kind = kScatter; d.J = J;
+                            const int r = next_s % rg.TQ;
+                            d.q = r / rg.T; t = r % rg.T;
+                            next_s += gridDim.x;
+                            break;
+                        }
+                    }
+                    if (next_n >= n_total && next_s >= s_total) break;                  // this CTA's tickets are done: exit
+                    // not runnable with the cached frontiers: re-read them; if they did not move, try to move them
+                    const uint4 c = ld_relaxed_v4(ctrl + kRingCtrlClaim);
+                    if ((int)c.z == sf && (int)c.w == cf) {
+                        if (!advance_frontiers(ctrl, sdone, ev, rg, sf, cf, lane)) {
+                            if (++spins > rg.spin_limit) { if (lane == 0) atomicOr(flag, 2u); }
+                            __nanosleep(64);
+                        }
+                        if (ld_relaxed_u32(flag) & 2u) break;                           // watchdog tripped somewhere: drain
+                    } else {
+                        sf = (int)c.z; cf = (int)c.w;
+                    }
                 }
-                t_raw = (lane == 0) ? atomicAdd(&ctrl[kRingCtrlTicket], 1u) : 0u;      // next ticket: in flight while this item is staged
-                if (!exists) continue;
+                STAT_ADD(8);
             }
-            const int slot = k % NSLOT, use = k / NSLOT;
-            if (k >= NSLOT) mbar_wait_wd(&bar_free[slot], (use - 1) & 1);
+            TRACE_T(1);
+            TRACE(6, (unsigned long long)d.kind);
             if (d.kind == kExit) {
                 if (lane == 0) { desc[slot] = d; mbar_arrive(&bar_posted[slot]); mbar_arrive(&bar_full[slot]); }
                 break;
@@ -354,68 +515,48 @@ __global__ void __launch_bounds__(ring::kThreads, 3) splat_ring_kernel(View4 in,
                 d.ylo = (jlo == 0) ? -1.f : (float)(jlo * R);
                 d.yhi = (jhi == rg.NS - 1) ? (float)g.H : (float)((jhi + 1) * R - 1);     // y0 + 1 must stay inside strip jhi
             }
+            // the item is claimed and decoded ahead of time; only now wait for its stage (k % NST: previous tenant was read)
+            if (d.kind == kScatter || (d.kind == kNorm && rg.Q == 1)) {
+                STAT_T0(); if (k >= NST) mbar_wait_wd(&bar_done[(k - NST) % NSLOT], ((k - NST) / NSLOT) & 1); STAT_ADD(7);
+            }
             if (d.kind == kScatter) {
                 const int sidx = k % NST;
-                if (k >= NST) mbar_wait_wd(&bar_done[(k - NST) % NSLOT], ((k - NST) / NSLOT) & 1);   // stage's previous tenant was read
                 const int hm = g.has_metric ? 1 : 0;
                 const int nch = max(0, min(4, g.C - d.q * 4));
-                const int nplanes = 2 + hm + nch;
-                const uint32_t row_bytes = (uint32_t)d.cols * 4u;
+                const int nbox = (rg.Q == 1) ? g.C : 4;               // channels per input box (fixed when the map was encoded)
+                float* sbase = stage + (size_t)sidx * STAGE_FLOATS;
                 if (lane == 0) {
                     desc[slot] = d;
-                    mbar_expect_tx(&bar_full[slot], row_bytes * (uint32_t)(nplanes * d.rows));
+                    mbar_expect_tx(&bar_full[slot], (uint32_t)((2 + hm + (nch > 0 ? nbox : 0)) * R * TW * 4));
+                    mbar_arrive(&bar_posted[slot]);
+                    tma_box_load(sbase, &tm_flow, &bar_full[slot], d.x0, d.yb, 0, d.n, pol);
+                    if (hm) tma_box_load(sbase + 2 * R * TW, &tm_metric, &bar_full[slot], d.x0, d.yb, 0, d.n, pol);
+                    if (nch > 0) tma_box_load(sbase + (2 + hm) * R * TW, &tm_in, &bar_full[slot], d.x0, d.yb, d.q * 4, d.n, pol);
+                    mbar_arrive(&bar_full[slot]);
+                }
+                __syncwarp();
+            } else if (d.kind == kNorm && rg.Q == 1) {
+                // single-quad splats: copy the strip's ring cells into the item's stage, so the consumers never wait for L2.
+                // The strip's producers are complete (the item holds a credit); their reductions went through the generic
+                // proxy, the copy reads through the async proxy.
+                fence_proxy_async_all();
+                const uint32_t row_bytes = (uint32_t)d.cols * 16u;
+                if (lane == 0) {
+                    desc[slot] = d;
+                    mbar_expect_tx(&bar_full[slot], row_bytes * (uint32_t)d.rows);
                     mbar_arrive(&bar_posted[slot]);
                 }
                 __syncwarp();
-                float* sbase = stage + (size_t)sidx * STAGE_FLOATS;
-                for (int i = lane; i < nplanes * R; i += 32) {
-                    const int p = i >> 3, r = i & 7;
-                    if (r < d.rows) {
-                        const float* src;
-                        const long long yoff = (long long)(d.yb + r);
-                        if (p < 2) src = flow.p + d.n * flow.sn + p * flow.sc + yoff * flow.sh + d.x0;
-                        else if (p < 2 + hm) src = metric.p + d.n * metric.sn + yoff * metric.sh + d.x0;
-                        else src = in.p + d.n * in.sn + (long long)(d.q * 4 + p - 2 - hm) * in.sc + yoff * in.sh + d.x0;
-                        bulk_load(sbase + (p * R + r) * TW, src, row_bytes, &bar_full[slot], pol);
-                    }
+                if (lane < d.rows) {
+                    const float4* src = ringbuf + (size_t)((d.row0 + d.yb + lane) & rg.mask) * rg.pitch + 1 + d.x0;
+                    bulk_load_plain(stage + (size_t)(k % NST) * STAGE_FLOATS + lane * TW * 4, src, row_bytes, &bar_full[slot]);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_full[slot]);
             } else {
                 if (lane == 0) { desc[slot] = d; mbar_arrive(&bar_posted[slot]); mbar_arrive(&bar_full[slot]); }
             }
-            ++k;
-        }
-    } else if (warp == kGateWarp) {
-        // ------------------------------------------------------------------ gatekeeper: dependency polls, one item ahead
-        for (int k = 0;; ++k) {
-            const int slot = k % NSLOT, use = k / NSLOT;
-            mbar_wait_wd(&bar_posted[slot], use & 1);
-            const int kind = desc[slot].kind, lo = desc[slot].dep_lo, hi = desc[slot].dep_hi;
-            if (kind == kScatter || kind == kNorm) {
-                int spins = 0;
-                for (;;) {
-                    bool ready = true;
-                    for (int JJ = lo + lane; JJ <= hi; JJ += 32) {
-                        if (kind == kScatter) {
-                            const unsigned need = (unsigned)(JJ / rg.RS + 1) * (unsigned)rg.T;
-                            if (ld_acquire_gpu(&clean[JJ % rg.RS]) < need) ready = false;
-                        } else {
-                            if (ld_acquire_gpu(&sdone[JJ]) < (unsigned)rg.TQ) ready = false;
-                        }
-                    }
-                    if (__all_sync(0xffffffffu, ready)) break;
-                    // watchdog: never hang the device - raise the flag (the guarded whole-frame launches re-do the call)
-                    if (++spins > rg.spin_limit || (ld_acquire_gpu(flag) & 2u)) {
-                        if (lane == 0) atomicOr(flag, 2u);
-                        break;
-                    }
-                    __nanosleep(64);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_full[slot]);
-            if (kind == kExit) break;
+            TRACE_T(2);
         }
     } else if (warp == kSignalWarp) {
         // ------------------------------------------------------------------ signaller: fence + completion counter
@@ -424,35 +565,52 @@ __global__ void __launch_bounds__(ring::kThreads, 3) splat_ring_kernel(View4 in,
             mbar_wait_wd(&bar_posted[slot], use & 1);
             const int kind = desc[slot].kind, J = desc[slot].J;
             if (kind == kExit) break;
-            mbar_wait_wd(&bar_done[slot], use & 1);
+            { STAT_T0(); mbar_wait_wd(&bar_done[slot], use & 1); STAT_ADD(10); }
+            STAT_T0();
+            // release: everything the consumers wrote (reductions, zero stores) is performed at L2 before the counter moves
+            // (CTA-scope barrier above, then one gpu-scope fence: the cooperative-groups grid.sync pattern)
+            int completed = 0;
             if (lane == 0) {
-                __threadfence();
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 if (kind == kScatter) {
                     if (s_ovf[slot]) { atomicOr(flag, 1u); s_ovf[slot] = 0; }
-                    red_add_u32(&sdone[J], 1u);
+                    completed = atomicAdd(&sdone[J], 1u) + 1u == (unsigned)rg.TQ;
                 } else if (kind == kNorm) {
-                    red_add_u32(&clean[J % rg.RS], 1u);
+                    completed = atomicAdd(&ev[rg.nZs + J], 1u) + 1u == (unsigned)rg.T;
                 } else {
-                    red_add_u32(&clean[J], 1u);
+                    completed = atomicAdd(&ev[J], 1u) + 1u == (unsigned)rg.T;
                 }
                 mbar_arrive(&bar_free[slot]);
             }
+            // the tile that completes a strip moves the frontier (and hands out the credits) right away
+            if (__shfl_sync(0xffffffffu, completed, 0)) {
+                const uint4 c = ld_relaxed_v4(ctrl + kRingCtrlClaim);
+                advance_frontiers(ctrl, sdone, ev, rg, (int)c.z, (int)c.w, lane);
+            }
             __syncwarp();
+            TRACE_T(5);
+            STAT_ADD(9);
         }
     } else {
         // ------------------------------------------------------------------ consumers
         const size_t plane = (size_t)rg.ring_rows * rg.pitch;
         for (int k = 0;; ++k) {
             const int slot = k % NSLOT, use = k / NSLOT;
-            mbar_wait_wd(&bar_full[slot], use & 1);
+            { STAT_T0(); mbar_wait_wd(&bar_full[slot], use & 1); STAT_ADD(0); }
             const ItemDesc d = desc[slot];
             if (d.kind == kExit) break;
+            if (warp == 0) TRACE_T(3);
+            STAT_T0();
             if (d.kind == kScatter) {
                 const float* st = stage + (size_t)(k % NST) * STAGE_FLOATS;
                 const bool ovf = ring_scatter_item<WKIND, PRE, QS, BOUNDED>(st, d, g, rg, ringbuf, tid, lane);
                 if (BOUNDED && __any_sync(0xffffffffu, ovf) && lane == 0) s_ovf[slot] = 1;
             } else if (d.kind == kNorm) {
-                ring_normalise_item(d, g, rg, ringbuf, out, norm_out, warp, lane);
+                if (rg.Q == 1)
+                    ring_normalise_item_staged(reinterpret_cast<const float4*>(stage + (size_t)(k % NST) * STAGE_FLOATS), d, g, rg,
+                                               ringbuf, out, norm_out, warp, lane);
+                else
+                    ring_normalise_item(d, g, rg, ringbuf, out, norm_out, warp, lane);
             } else {
                 // Z: cells 1 .. W of the slot's 8 rows, every quad
                 if (tid < d.cols)
@@ -463,6 +621,8 @@ __global__ void __launch_bounds__(ring::kThreads, 3) splat_ring_kernel(View4 in,
                     }
             }
             __syncwarp();
+            if (warp == 0) TRACE_T(4);
+            STAT_ADD(d.kind == kScatter ? 1 : 2);
             if (lane == 0) mbar_arrive(&bar_done[slot]);
         }
     }
@@ -507,38 +667,38 @@ void plan_ring(const SplatGeom& g, RingPlan& p) {
     rg.ring_rows = (int)rows;
     rg.mask = whole ? -1 : (int)rows - 1;
     rg.TQ = rg.T * rg.Q;
-    rg.GI = rg.TQ + rg.T;
     const int lag_opt = get_option(kOptSplatLag);
     if (whole) {
         rg.bounded = 0;
         rg.Ds = rg.NS;
-        rg.D2 = (rg.NS - 1) + (lag_opt > 0 ? lag_opt : 2);
     } else {
-        // Tickets are handed out in order and every CTA holds up to NST of them, so an item completes within about
-        // `gif` groups of ticket progress.  N(J) is handed out `lag` groups after its last producer S(J+Ds), and the ring
-        // slot of strip J+Ds is not needed again before its previous tenant's N is `lag` groups old as well:
-        //   RS >= 2 Ds + 2 lag
-        const int ctas = sm_count() * 3;
-        const int gif = (ctas * NST + rg.GI - 1) / rg.GI;
-        const int lag = lag_opt > 0 ? lag_opt : (gif < 4 ? 4 : gif);
+        // The ring holds 2 Ds strips of reach plus the strips in flight between the normalise frontier and the scatter
+        // head: S(J) is claimable once the slot of strip J + Ds was cleaned (N(J + Ds - RS) done) and N(J) once
+        // S(J + Ds) is done, so scatter runs at most RS - 2 Ds = 2 lag strips ahead of what normalise has retired.
+        const int lag = lag_opt > 0 ? lag_opt : 12;
         rg.bounded = 1;
         rg.Ds = (rg.RS - 2 * lag) / 2;
         if (rg.Ds < 1) p.ok = false;
-        rg.D2 = rg.Ds + lag;
     }
-    rg.nZ = (int)(rg.RS < NT ? rg.RS : NT) * rg.T;
-    const long long total = (long long)rg.nZ + (NT + rg.D2) * rg.GI;
-    if (total >= (1ll << 31)) p.ok = false;
+    rg.nZs = (int)(rg.RS < NT ? rg.RS : NT);
+    rg.nZ = rg.nZs * rg.T;
+    const long long total = (long long)rg.nZ + NT * rg.T + NT * rg.TQ;
+    if (total >= (1ll << 30)) p.ok = false;
     rg.total = (int)total;
     rg.spin_limit = 1 << 18;
     p.ring_bytes = align_up((size_t)rows * row_bytes, 256);
-    p.ctrl_bytes = align_up(((size_t)kRingCtrlCounters + (size_t)NT + rg.RS) * 4, 256);
+    p.ctrl_bytes = align_up(((size_t)kRingCtrlCounters + (size_t)NT + rg.nZs + (size_t)NT) * 4, 256);
+#ifdef FLDR_RING_TRACE
+    p.ctrl_bytes += 8 * 128 * 8 * 8 + 256;
+#endif
     if (!p.ok) { p.ring_bytes = 0; p.ctrl_bytes = 256; }
 }
 
+struct RingMaps { CUtensorMap in, flow, metric; };
+
 template <int WKIND, bool PRE, int QS, bool BOUNDED>
-static int launch_ring_t(const RingPlan& p, const SplatGeom& g, const View4& in, const View4& flow, const View4& metric,
-                         void* ringbuf, unsigned* ctrl, float* out, float* norm, cudaStream_t s) {
+static int launch_ring_t(const RingPlan& p, const SplatGeom& g, const RingMaps& m, void* ringbuf, unsigned* ctrl, float* out,
+                         float* norm, cudaStream_t s) {
     auto fn = splat_ring_kernel<WKIND, PRE, QS, BOUNDED>;
     // per-instantiation, per-device launch state (attribute set + occupancy), computed once
     static int ctas_per_sm[64] = {0};
@@ -551,18 +711,38 @@ static int launch_ring_t(const RingPlan& p, const SplatGeom& g, const View4& in,
         if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, ring::kThreads, ring::kSmemBytes) != cudaSuccess || nb < 1) nb = 1;
-        per_sm = nb > 3 ? 3 : nb;
+        per_sm = nb > ring::kCtasPerSm ? ring::kCtasPerSm : nb;
         __atomic_store_n(&ctas_per_sm[dev], per_sm, __ATOMIC_RELEASE);
     }
     long long grid = (long long)sm_count() * per_sm;
     if (grid > p.rg.total) grid = p.rg.total;
-    fn<<<(unsigned)grid, ring::kThreads, ring::kSmemBytes, s>>>(in, flow, metric, reinterpret_cast<float4*>(ringbuf), ctrl, out, norm,
-                                                                g, p.rg);
+    fn<<<(unsigned)grid, ring::kThreads, ring::kSmemBytes, s>>>(m.in, m.flow, m.metric, reinterpret_cast<float4*>(ringbuf), ctrl, out,
+                                                                norm, g, p.rg);
     return check_launch();
 }
 
+// [N][C][H][W] view -> 4-D tensor map with an [nbox][8][128] box
+static bool encode_view(CUtensorMap* map, const View4& v, int N, int C, int H, int W, int nbox) {
+    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)N};
+    const uint64_t strides[3] = {(uint64_t)v.sh * 4, (uint64_t)v.sc * 4, (uint64_t)v.sn * 4};
+    const uint32_t box[4] = {(uint32_t)ring::TW, (uint32_t)ring::R, (uint32_t)nbox, 1u};
+    if (v.sh <= 0 || v.sc <= 0 || v.sn <= 0) return false;
+    return encode_tensor_map_4d(map, v.p, dims, strides, box);
+}
+
+// Returns FLDR_ERR_UNSUPPORTED when the views cannot be described by tensor maps (the caller then takes the whole-frame path).
 int launch_ring(const RingPlan& p, const SplatGeom& g, const View4& in, const View4& flow, const View4& metric, void* ringbuf,
                 unsigned* ctrl, float* out, float* norm, cudaStream_t s) {
+    RingMaps m;
+    const int nbox = (p.rg.Q == 1) ? g.C : 4;
+    View4 vin = in, vfl = flow, vme = metric;
+    // single-sample / single-channel dimensions: any positive 16-byte-multiple stride describes them
+    if (g.N == 1) { vin.sn = (long long)g.C * g.H * g.W + 4; vfl.sn = 2ll * g.H * g.W + 4; vme.sn = (long long)g.H * g.W + 4; vin.sn -= vin.sn % 4; vfl.sn -= vfl.sn % 4; vme.sn -= vme.sn % 4; }
+    if (g.C == 1) vin.sc = ((long long)g.H * g.W + 4) / 4 * 4;
+    vme.sc = ((long long)g.H * g.W + 4) / 4 * 4;
+    if (!encode_view(&m.in, vin, g.N, g.C, g.H, g.W, nbox) || !encode_view(&m.flow, vfl, g.N, 2, g.H, g.W, 2)) return FLDR_ERR_UNSUPPORTED;
+    if (g.has_metric) { if (!encode_view(&m.metric, vme, g.N, 1, g.H, g.W, 1)) return FLDR_ERR_UNSUPPORTED; }
+    else m.metric = m.flow;
     cudaError_t e = cudaMemsetAsync(ctrl, 0, p.ctrl_bytes, s);
     if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
     const int wkind = !g.has_metric ? 0 : (g.mode == FLDR_SPLAT_SOFTMAX ? 1 : 2);
@@ -570,8 +750,8 @@ int launch_ring(const RingPlan& p, const SplatGeom& g, const View4& in, const Vi
     const int qs = (g.C == 3 && g.CA == 4) ? 1 : (g.CA == g.C && g.C % 4 == 0) ? 2 : 0;
     const bool b = p.rg.bounded != 0;
 #define FLDR_RING3(WK_, PRE_, QS_) \
-    (b ? launch_ring_t<WK_, PRE_, QS_, true>(p, g, in, flow, metric, ringbuf, ctrl, out, norm, s) \
-       : launch_ring_t<WK_, PRE_, QS_, false>(p, g, in, flow, metric, ringbuf, ctrl, out, norm, s))
+    (b ? launch_ring_t<WK_, PRE_, QS_, true>(p, g, m, ringbuf, ctrl, out, norm, s) \
+       : launch_ring_t<WK_, PRE_, QS_, false>(p, g, m, ringbuf, ctrl, out, norm, s))
 #define FLDR_RING2(WK_, PRE_) (qs == 1 ? FLDR_RING3(WK_, PRE_, 1) : qs == 2 ? FLDR_RING3(WK_, PRE_, 2) : FLDR_RING3(WK_, PRE_, 0))
     if (wkind == 1) return FLDR_RING2(1, true);
     if (wkind == 2) return FLDR_RING2(2, false);
