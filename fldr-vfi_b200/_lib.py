@@ -20,7 +20,6 @@ SYMBOLS = {
     "fldr_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "fldr_get_option": (ctypes.c_int, [ctypes.c_char_p]),
     "fldr_splat_fwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 5),
-    "fldr_splat_fwd_plan": (ctypes.c_int, [ctypes.c_int] * 6 + [c_i64_p]),
     "fldr_splat_fwd": (ctypes.c_int, [ctypes.c_int, c_float_p, c_i64_p, c_float_p, c_i64_p, c_float_p, c_i64_p,
                                       c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),

@@ -27,9 +27,9 @@ int sm_count() {
 }  // namespace fldr
 
 namespace fldr {
-static const char* const kOptionNames[kOptCount] = {"splat_stream", "splat_ring_mb", "splat_lag", "splat_fused_max", "corr_th", "splat_pf_rows"};
-static const char* const kOptionEnv[kOptCount] = {"FLDR_SPLAT_STREAM", "FLDR_SPLAT_RING_MB", "FLDR_SPLAT_LAG", "FLDR_SPLAT_FUSED_MAX", "FLDR_CORR_TH", "FLDR_SPLAT_PF_ROWS"};
-static const int kOptionDefault[kOptCount] = {1, 0, 0, 40000, 0, 0};
+static const char* const kOptionNames[kOptCount] = {"splat_tma", "splat_fused_max", "corr_th", "splat_pf_rows"};
+static const char* const kOptionEnv[kOptCount] = {"FLDR_SPLAT_TMA", "FLDR_SPLAT_FUSED_MAX", "FLDR_CORR_TH", "FLDR_SPLAT_PF_ROWS"};
+static const int kOptionDefault[kOptCount] = {1, 40000, 0, 0};
 static int g_options[kOptCount];
 static std::once_flag g_options_once;
 static void init_options() {

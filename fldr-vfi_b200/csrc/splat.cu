@@ -6,19 +6,21 @@
 //
 // Data layout in HBM
 //   inputs      NCHW fp32 with arbitrary element strides (callers pass views: fLDRnet.py:386,449)
-//   accumulator [N][Q][H][W][4] fp32, Q = ceil((C + has_norm) / 4): every channel quad is a pixel-interleaved
-//               float4 image, so one corner of one source pixel is ONE 16-byte red.global.add.v4.f32 and adjacent
+//   accumulator [N][Q][H][W + 2][4] fp32, Q = ceil((C + has_norm) / 4): every channel quad is a pixel-interleaved
+//               float4 image with one guard cell either side of a row (corners one column outside the frame land
+//               there and are never read: no x test on the reductions), so one corner of one source pixel is ONE 16-byte red.global.add.v4.f32 and adjacent
 //               lanes (adjacent x) reduce into adjacent slots (the reference issues 4 scalar REDs per element,
 //               softSplat.py:39-50).  The normaliser rides in slot C % 4 of quad C / 4.
 //   outputs     NCHW contiguous (what the reference allocates, softSplat.py:234).
 //
 // Paths (fldr_splat_fwd picks; DESIGN.md section 4.1 has the measurements behind each choice)
 //   tiny frames    splat_fused_small_kernel: zero + scatter + normalise in one cooperative launch
-//   default        splat_ring_kernel (splat_ring.cu): one launch, L2-resident ring accumulator, dataflow counters;
-//                  when the ring is smaller than the batch its vertical reach is bounded and the whole-frame launches
-//                  below follow it, guarded by a device flag (they exit at once unless a source left the reach)
-//   whole frame    cudaMemsetAsync + splat_scatter_merged_kernel + splat_normalise_kernel: views the ring kernel's bulk
-//                  copies cannot take (W % 4 != 0, unaligned or non-unit-stride rows), "splat_stream" = 0, the fallback
+//   default        cudaMemsetAsync + splat_scatter_tile_kernel (inputs staged by TMA, lean merged-reduction body)
+//                  + splat_normalise_kernel
+//   odd views      the same three passes with splat_scatter_merged_kernel (plain loads): rows that are not 16-byte aligned,
+//                  non-unit pixel stride, metric together with >= 4 channels
+// (A single-launch streaming variant with an L2-resident ring accumulator was built and measured in round 2; it moved
+//  322 MB instead of 848 MB through DRAM but lost on time - profiles/r2_splat_streaming_negative_result.txt.)
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -26,6 +28,7 @@
 #include <cooperative_groups.h>
 
 #include "splat.cuh"
+#include "tma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -92,11 +95,11 @@ template <> __device__ __forceinline__ void vstore<4>(float* p, const float* t) 
     __stcs(reinterpret_cast<float4*>(p), make_float4(t[0], t[1], t[2], t[3]));
 }
 
-// Whole-frame accumulator plane [H][W] float4 of one (sample, quad).
+// Whole-frame accumulator plane [H][W + 2] float4 of one (sample, quad); pixel x lives in cell x + 1.
 struct PlaneAcc {
     float4* base;
-    int W;
-    __device__ __forceinline__ float4* at(int x, int y) const { return base + (y * W + x); }
+    int W, P;           // frame width, row pitch in cells (W + 2)
+    __device__ __forceinline__ float4* at(int x, int y) const { return base + (y * P + x + 1); }
     // The whole-frame accumulator lives in DRAM; a reduction into a line that is not in L2 stalls the L2 reduction unit
     // on the fill.  Pulling the target lines of the rows this thread will reach next into L2 ahead of time turns those
     // fills into ordinary, well-pipelined reads.
@@ -104,7 +107,7 @@ struct PlaneAcc {
     __device__ __forceinline__ int prefetch_rows() const { return pf_rows; }
     __device__ __forceinline__ void prefetch(int x, int y) const {
         if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (y * W + x)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (y * P + x + 1)));
     }
 };
 
@@ -242,18 +245,169 @@ __device__ __forceinline__ void scatter_rows(const View4& in, const View4& flow,
 
 template <int WKIND, bool PRE, int QS>
 __global__ void __launch_bounds__(128, FLDR_SCATTER_MIN_CTAS) splat_scatter_merged_kernel(View4 in, View4 flow, View4 metric,
-                                                                   float* __restrict__ acc, SplatGeom g, int Q,
-                                                                   const unsigned* __restrict__ guard, int pf_rows, int R) {
-    if (guard && *guard == 0) return;      // fallback launch that turned out not to be needed
+                                                                   float* __restrict__ acc, SplatGeom g, int Q, int pf_rows, int R) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int yb = blockIdx.y * R;
     const int q = blockIdx.z % Q, n = blockIdx.z / Q;
     PlaneAcc pa;
-    pa.base = reinterpret_cast<float4*>(acc) + (long long)(n * Q + q) * g.H * g.W;
+    pa.P = g.W + 2;
+    pa.base = reinterpret_cast<float4*>(acc) + (long long)(n * Q + q) * g.H * pa.P;
     pa.W = g.W;
     pa.H = g.H;
     pa.pf_rows = pf_rows;
     scatter_rows<WKIND, PRE, QS>(in, flow, metric, g, n, q, x, yb, min(R, g.H - yb), pa);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pass 1, default: tile kernel.  A CTA owns 8 source rows x 128 columns of one channel quad.  Thread 0 stages the tile's
+// inputs in shared memory with two or three TMA box loads ([planes][8][128]; rows / columns / channels outside the
+// tensor are zero-filled by the TMA unit), so the walk below has no address arithmetic on the inputs and never waits for
+// DRAM row by row (the other resident CTAs cover the one load latency per tile).
+// The walk is the merged-reduction scheme of scatter_rows in a leaner form (144 instead of 227 instructions per
+// warp-row): a corner is identified by its accumulator CELL OFFSET (negative = not in frame), two corners merge iff they
+// are the same memory cell, and the guard cells of the row pitch remove every x test from the reductions.
+// ------------------------------------------------------------------------------------------------
+namespace tile {
+constexpr int R = 8, TW = 128, PLANES = 6;
+constexpr int kSent = -(1 << 30);             // "no cell": stays negative after + 1
+}  // namespace tile
+
+// one [planes][8 rows][128 columns] box of an NCHW input, global -> shared; the inputs are read exactly once: evict-first in L2
+__device__ __forceinline__ void tma_box_load(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int c, int n, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(c), "r"(n), "l"(pol)
+        : "memory");
+}
+// cell `off` of plane `base` += v, only when off >= 0
+__device__ __forceinline__ void red4_at(float4* base, int off, const float* v) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u64 a;\n\t"
+        "setp.ge.s32 p, %1, 0;\n\t"
+        "mad.wide.s32 a, %1, 16, %0;\n\t"
+        "@p red.global.add.v4.f32 [a], {%2, %3, %4, %5};\n\t}"
+        ::"l"(base), "r"(off), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]));
+}
+__device__ __forceinline__ void prefetch_l2_at(float4* base, int off) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u64 a;\n\t"
+        "setp.ge.s32 p, %1, 0;\n\t"
+        "mad.wide.s32 a, %1, 16, %0;\n\t"
+        "@p prefetch.global.L2 [a];\n\t}"
+        ::"l"(base), "r"(off));
+}
+// e^z to ~2 ulp for any z: ex2.approx of the rounded product, corrected by the product's rounding error and the
+// representation error of log2(e) (the plain ex2(z * log2e) loses |z| * 6e-8 relative; expf costs twice the instructions)
+__device__ __forceinline__ float exp_splat(float z) {
+    const float l2e = 1.4426950408889634f;
+    const float t = z * l2e;
+    const float e = fmaf(z, l2e, -t) + z * 1.92596299e-8f;
+    float p;
+    asm("ex2.approx.f32 %0, %1;" : "=f"(p) : "f"(t));
+    return fmaf(p, e * 0.6931471805599453f, p);
+}
+
+template <int WKIND, bool PRE, int QS>
+__global__ void __launch_bounds__(tile::TW, 6) splat_scatter_tile_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                                         const __grid_constant__ CUtensorMap tm_flow,
+                                                                         const __grid_constant__ CUtensorMap tm_metric,
+                                                                         float* __restrict__ acc, SplatGeom g, int Q, int nbox,
+                                                                         int pf_rows) {
+    using namespace tile;
+    __shared__ __align__(128) float st[PLANES * R * TW];
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int x0 = blockIdx.x * TW, yb = blockIdx.y * R;
+    const int q = blockIdx.z % Q, n = blockIdx.z / Q;
+    const int nch = QS == 1 ? 3 : QS == 2 ? 4 : min(4, g.C - q * 4);
+    const int wslot = QS == 1 ? 3 : QS == 2 ? -1 : ((g.CA > g.C) ? g.C - q * 4 : -1);
+    constexpr int HM = WKIND ? 1 : 0, CH0 = 2 + HM;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        mbar_arrive_expect_tx(&bar, (uint32_t)((2 + HM + (nch > 0 ? nbox : 0)) * R * TW * 4));
+        tma_box_load(st, &tm_flow, &bar, x0, yb, 0, n, pol);
+        if (HM) tma_box_load(st + 2 * R * TW, &tm_metric, &bar, x0, yb, 0, n, pol);
+        if (nch > 0) tma_box_load(st + CH0 * R * TW, &tm_in, &bar, x0, yb, q * 4, n, pol);
+    }
+    __syncthreads();                                   // barrier initialised before anyone waits on it
+    const int rows = min(R, g.H - yb), P = g.W + 2;
+    float4* rq = reinterpret_cast<float4*>(acc) + (size_t)(n * Q + q) * g.H * P;
+    const bool inb = x0 + tid < g.W;
+    const float Wf = (float)g.W, Hf = (float)g.H, Hm1 = (float)(g.H - 1);
+    const float xf = (float)(x0 + tid);
+    float yf = (float)yb;
+    const int src_lane = (lane + 31) & 31;
+    const bool lane_gt0 = lane > 0;
+    const int pfo = pf_rows * P;
+    int prev_t = kSent;
+    float pw[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* sp = st + tid;
+    mbar_wait(&bar, 0);
+#pragma unroll 2
+    for (int r = 0; r < rows; ++r, yf += 1.f, sp += TW) {
+        const float u = sp[0], v = sp[R * TW];
+        float m = 1.f;
+        if (WKIND == 1) m = exp_splat(sp[2 * R * TW]);
+        if (WKIND == 2) m = sp[2 * R * TW];
+        float xv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xv[j] = (j < nch) ? sp[(CH0 + j) * R * TW] : 0.f;
+        // softSplat.py:23-38
+        const float X = xf + u, Y = yf + v;
+        const float fx0 = floorf(X), fy0 = floorf(Y);
+        const float x1f = fx0 + 1.f, y1f = fy0 + 1.f;
+        const bool pR = inb && fx0 >= -1.f && fx0 < Wf && fy0 >= -1.f && fy0 < Hf;   // false for NaN / inf (the reference asserts, 25-26)
+        const bool pT = pR && fy0 >= 0.f;                        // top corners in frame
+        const bool pB = pR && fy0 < Hm1;                         // bottom corners in frame
+        const int cx = (int)x1f;                                 // x0 + 1 = cell of the W corners (guard cell at 0)
+        const int y0 = (int)fy0;
+        const int tT = pT ? y0 * P + cx : kSent;
+        const int tB = pB ? (y0 + 1) * P + cx : kSent;
+        if (pfo) prefetch_l2_at(rq, pR && fy0 + (float)pf_rows < Hm1 ? (y0 + 1) * P + cx + pfo : kSent);
+        const float ax = x1f - X, bx = X - fx0, ay = y1f - Y, by = Y - fy0;
+        const float wNW = ax * ay, wNE = bx * ay, wSW = ax * by, wSE = bx * by;
+        // a corner that is not in frame keeps whatever this arithmetic produces (NaN included): it is never merged into a
+        // valid corner (cell offsets differ) and never issued
+        const float hm = PRE ? 0.5f * m : m;                     // ((x+1)*0.5)*m == (x+1)*(0.5*m) exactly
+        float tW[4], tE[4], bW[4], bE[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a;
+            if (j < nch) a = PRE ? (xv[j] + 1.f) * hm : xv[j] * m;
+            else a = (j == wslot) ? m : 0.f;
+            tW[j] = a * wNW; tE[j] = a * wNE; bW[j] = a * wSW; bE[j] = a * wSE;
+        }
+        // vertical: the bottom-W corner carried from the previous row joins this row's top-W corner, or is flushed
+        const bool vm = tT == prev_t;
+        red4_at(rq, vm ? kSent : prev_t, pw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tW[j] = vm ? tW[j] + pw[j] : tW[j];
+        // horizontal: the E corners travel to the lane on the right (rotate: lane 0 gets lane 31's and only forwards them)
+        const int rT = __shfl_sync(0xffffffffu, tT + 1, src_lane);
+        const int rB = __shfl_sync(0xffffffffu, tB + 1, src_lane);
+        float rt4[4], rb4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            rt4[j] = __shfl_sync(0xffffffffu, tE[j], src_lane);
+            rb4[j] = __shfl_sync(0xffffffffu, bE[j], src_lane);
+        }
+        const bool takeT = lane_gt0 && rT == tT, takeB = lane_gt0 && rB == tB;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            tW[j] = takeT ? tW[j] + rt4[j] : tW[j];
+            bW[j] = takeB ? bW[j] + rb4[j] : bW[j];
+        }
+        red4_at(rq, takeT ? kSent : rT, rt4);
+        red4_at(rq, takeB ? kSent : rB, rb4);
+        red4_at(rq, tT, tW);
+        prev_t = tB;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pw[j] = bW[j];
+    }
+    red4_at(rq, prev_t, pw);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -262,19 +416,21 @@ __global__ void __launch_bounds__(128, FLDR_SCATTER_MIN_CTAS) splat_scatter_merg
 //   softSplat.py:343-349: norm==0 -> 1, divide, (y - 0.5) * 2 (post-scale in every mode but RAW).
 // ------------------------------------------------------------------------------------------------
 template <int PX>
-__global__ void __launch_bounds__(256) splat_normalise_kernel(const float* __restrict__ acc, float* __restrict__ out,
-                                                              float* __restrict__ norm_out, SplatGeom g, int Q,
-                                                              const unsigned* __restrict__ guard) {
-    if (guard && *guard == 0) return;      // fallback launch that turned out not to be needed
+__global__ void __launch_bounds__(128) splat_normalise_kernel(const float* __restrict__ acc, float* __restrict__ out,
+                                                              float* __restrict__ norm_out, SplatGeom g, int Q) {
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
+    if (x >= g.W) return;       // PX > 1 only when W % PX == 0
+    const int y = blockIdx.y;
+    const int q = blockIdx.z % Q, n = blockIdx.z / Q;
     const long long HW = (long long)g.H * g.W;
-    const long long pix = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * PX;
-    if (pix >= HW) return;      // PX > 1 only when HW % PX == 0
-    const int q = blockIdx.y % Q, n = blockIdx.y / Q;
+    const long long pix = (long long)y * g.W + x;
+    const int P = g.W + 2;
     const bool has_norm = g.CA > g.C;
-    const float4* accn = reinterpret_cast<const float4*>(acc) + (long long)n * Q * HW;
+    const float4* row = reinterpret_cast<const float4*>(acc) + ((long long)n * Q * g.H + y) * P + 1 + x;     // quad 0 of this row
+    const long long qstride = (long long)g.H * P;
     float4 s4[PX];
 #pragma unroll
-    for (int k = 0; k < PX; ++k) s4[k] = __ldcs(accn + q * HW + pix + k);
+    for (int k = 0; k < PX; ++k) s4[k] = __ldcs(row + q * qstride + k);
     float d[PX];
 #pragma unroll
     for (int k = 0; k < PX; ++k) d[k] = 1.f;
@@ -283,9 +439,9 @@ __global__ void __launch_bounds__(256) splat_normalise_kernel(const float* __res
         float nrm[PX];
 #pragma unroll
         for (int k = 0; k < PX; ++k) {
-            const float4 n4 = (qn == q) ? s4[k] : __ldcs(accn + qn * HW + pix + k);
+            const float4 n4 = (qn == q) ? s4[k] : __ldcs(row + qn * qstride + k);
             nrm[k] = slot == 0 ? n4.x : slot == 1 ? n4.y : slot == 2 ? n4.z : n4.w;
-            d[k] = norm_recip(nrm[k]);     // hole fix-up + one IEEE reciprocal per pixel (splat.cuh)
+            d[k] = norm_recip(nrm[k]);     // hole fix-up + one reciprocal per pixel (splat.cuh)
         }
         if (norm_out && q == 0) vstore<PX>(norm_out + (long long)n * HW + pix, nrm);
     }
@@ -305,13 +461,6 @@ __global__ void __launch_bounds__(256) splat_normalise_kernel(const float* __res
     }
 }
 
-// guarded zero fill for the whole-frame fallback (a cudaMemsetAsync cannot be made conditional on a device flag)
-__global__ void __launch_bounds__(256) splat_zero_kernel(float4* __restrict__ p, long long n4, const unsigned* __restrict__ guard) {
-    if (guard && *guard == 0) return;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
-        p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
 // ------------------------------------------------------------------------------------------------
 // Small frames: zero + scatter + normalise in ONE cooperative launch (two grid barriers instead of two kernel
 // boundaries and a memset).  The pyramid's small splats (C = 48 at 144x256 ... 18x32) are launch-latency bound:
@@ -325,11 +474,13 @@ __global__ void __launch_bounds__(256) splat_fused_small_kernel(View4 in, View4 
     cg::grid_group grid = cg::this_grid();
     const long long HW = (long long)g.H * g.W;
     const long long n4 = (long long)g.N * Q * HW;
+    const int P = g.W + 2;
+    const long long HP = (long long)g.H * P;               // cells per (sample, quad) plane
     const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long gthreads = (long long)gridDim.x * blockDim.x;
     float4* acc4 = reinterpret_cast<float4*>(acc);
-    // ---- A: zero the accumulator
-    for (long long i = gtid; i < n4; i += gthreads) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- A: zero the accumulator (guard cells included)
+    for (long long i = gtid; i < (long long)g.N * Q * HP; i += gthreads) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     grid.sync();
     // ---- B: scatter, one unit per warp
     {
@@ -342,8 +493,9 @@ __global__ void __launch_bounds__(256) splat_fused_small_kernel(View4 in, View4 
             const int nq = (int)(u / ((long long)cblocks * runs));
             const int q = nq % Q, n = nq / Q;
             PlaneAcc pa;
-            pa.base = acc4 + (long long)nq * HW;
+            pa.base = acc4 + (long long)nq * HP;
             pa.W = g.W;
+            pa.P = P;
             pa.H = g.H;
             pa.pf_rows = 0;      // small frames: the accumulator is L2-resident anyway
             const int yb = run * R;
@@ -359,10 +511,11 @@ __global__ void __launch_bounds__(256) splat_fused_small_kernel(View4 in, View4 
             const long long pix = i % HW;
             const int nq = (int)(i / HW);
             const int q = nq % Q, n = nq / Q;
-            const float4 s4 = __ldcg(acc4 + i);
+            const long long cell = (pix / g.W) * P + 1 + (pix % g.W);      // inside a plane
+            const float4 s4 = __ldcg(acc4 + nq * HP + cell);
             float d = 1.f;
             if (has_norm) {
-                const float4 n4v = (qn == q) ? s4 : __ldcg(acc4 + ((long long)n * Q + qn) * HW + pix);
+                const float4 n4v = (qn == q) ? s4 : __ldcg(acc4 + ((long long)n * Q + qn) * HP + cell);
                 const float nrm = slot == 0 ? n4v.x : slot == 1 ? n4v.y : slot == 2 ? n4v.z : n4v.w;
                 if (norm_out && q == 0) norm_out[(long long)n * HW + pix] = nrm;
                 d = norm_recip(nrm);
@@ -508,33 +661,15 @@ static unsigned grid_for(long long total, int block) {
 struct FwdPlan {
     SplatGeom g;
     int Q;
-    RingPlan ring;        // streaming path (ring.ok: usable for this shape)
-    size_t ring_bytes, ctrl_bytes, full_bytes, total_bytes;     // workspace regions, in this order
+    size_t acc_bytes;       // accumulator [N][Q][H][W + 2] float4
 };
-
-// Workspace layout: [ring | ctrl | whole-frame accumulator].  Sizes depend on the shape only (the ring region is sized for
-// the largest ring the "splat_ring_mb" option may select), so a size queried once per shape stays valid.
-static const int kRingMbMax = 72;
 
 static int plan_fwd(int mode, int N, int C, int H, int W, bool has_metric, FwdPlan& p) {
     int st = make_geom(mode, N, C, H, W, has_metric, p.g);
     if (st != FLDR_OK) return st;
     p.Q = p.g.CP / 4;
-    p.full_bytes = align_up((size_t)N * p.Q * H * W * 16, 256);
-    plan_ring(p.g, p.ring);
-    // region sizes: as if the ring were at its cap
-    const size_t row_bytes = (size_t)(W + 2) * 16 * p.Q;
-    size_t rows = (size_t)N * ((H + 7) / 8) * 8;
-    size_t cap_rows = 64;
-    while (cap_rows * 2 * row_bytes <= ((size_t)kRingMbMax << 20)) cap_rows *= 2;
-    if (rows * row_bytes > ((size_t)kRingMbMax << 20) && rows > cap_rows) rows = cap_rows;
-    p.ring_bytes = align_up(rows * row_bytes, 256);
-    p.ctrl_bytes = align_up(((size_t)kRingCtrlCounters + 2 * (size_t)N * ((H + 7) / 8) + rows / 8) * 4, 256);
-#ifdef FLDR_RING_TRACE
-    p.ctrl_bytes += 8 * 128 * 8 * 8 + 256;
-#endif
-    if (p.ring.ok && (p.ring.ring_bytes > p.ring_bytes || p.ring.ctrl_bytes > p.ctrl_bytes)) p.ring.ok = false;
-    p.total_bytes = p.ring_bytes + p.ctrl_bytes + p.full_bytes;
+    if ((long long)H * (W + 2) >= (1ll << 30)) return FLDR_ERR_UNSUPPORTED;       // 32-bit cell offsets inside a plane
+    p.acc_bytes = align_up((size_t)N * p.Q * H * (W + 2) * 16, 256);
     return FLDR_OK;
 }
 
@@ -545,53 +680,68 @@ using namespace fldr;
 extern "C" size_t fldr_splat_fwd_workspace_bytes(int mode, int N, int C, int H, int W) {
     FwdPlan p;
     if (plan_fwd(mode, N, C, H, W, true, p) != FLDR_OK) return 0;
-    return p.total_bytes;
+    return p.acc_bytes;
 }
 
-static int launch_normalise(const FwdPlan& p, float* acc, float* out, float* norm, const unsigned* guard, cudaStream_t s) {
+static int launch_normalise(const FwdPlan& p, float* acc, float* out, float* norm, cudaStream_t s) {
     const SplatGeom& g = p.g;
     const int N = g.N, Q = p.Q;
-    const long long HW = (long long)g.H * g.W;
-    const bool px4 = (HW % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+    const bool px4 = (g.W % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                      (!norm || (reinterpret_cast<uintptr_t>(norm) & 15) == 0);
     if (px4) {
-        dim3 grid((unsigned)((HW / 4 + 255) / 256), N * Q, 1);
-        splat_normalise_kernel<4><<<grid, 256, 0, s>>>(acc, out, norm, g, Q, guard);
+        dim3 grid((unsigned)((g.W / 4 + 127) / 128), g.H, N * Q);
+        splat_normalise_kernel<4><<<grid, 128, 0, s>>>(acc, out, norm, g, Q);
     } else {
-        dim3 grid((unsigned)((HW + 255) / 256), N * Q, 1);
-        splat_normalise_kernel<1><<<grid, 256, 0, s>>>(acc, out, norm, g, Q, guard);
+        dim3 grid((unsigned)((g.W + 127) / 128), g.H, N * Q);
+        splat_normalise_kernel<1><<<grid, 128, 0, s>>>(acc, out, norm, g, Q);
     }
     return check_launch();
 }
 
-// whole-frame path: zero + merged scatter + normalise.  `guard` (device flag) makes the three launches no-ops unless set.
-static int launch_whole_frame(const FwdPlan& p, const View4& vin, const View4& vfl, const View4& vme, float* acc, float* out,
-                              float* norm, const unsigned* guard, cudaStream_t s) {
+// Can the TMA tile kernel take these views?  (16-byte aligned rows / planes, unit pixel stride, at most 6 staged planes)
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static bool view_tma_ok(const View4& v) {
+    return v.sw == 1 && v.sh > 0 && v.sc > 0 && v.sn > 0 && (v.sh % 4) == 0 && (v.sc % 4) == 0 && (v.sn % 4) == 0 && aligned16(v.p);
+}
+// [N][C][H][W] view -> 4-D tensor map with an [nbox][8][128] box
+static bool encode_view(CUtensorMap* map, const View4& v, int N, int C, int H, int W, int nbox) {
+    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)N};
+    const uint64_t strides[3] = {(uint64_t)v.sh * 4, (uint64_t)v.sc * 4, (uint64_t)v.sn * 4};
+    const uint32_t box[4] = {(uint32_t)tile::TW, (uint32_t)tile::R, (uint32_t)nbox, 1u};
+    return encode_tensor_map_4d(map, v.p, dims, strides, box);
+}
+
+// zero + scatter + normalise
+static int launch_forward(const FwdPlan& p, const View4& vin, const View4& vfl, const View4& vme, float* acc, float* out,
+                          float* norm, cudaStream_t s) {
     const SplatGeom& g = p.g;
     const int N = g.N, H = g.H, W = g.W, Q = p.Q;
     int st;
-    if ((long long)N * Q > 65535) return FLDR_ERR_UNSUPPORTED;
+    if ((long long)N * Q > 65535 || H > 65535) return FLDR_ERR_UNSUPPORTED;
     const long long n4 = (long long)N * Q * H * W;
-    if (!guard && n4 <= (long long)get_option(kOptSplatFusedMax) && get_option(kOptSplatFusedMax) > 0) {
+    const int wkind = !g.has_metric ? 0 : (g.mode == FLDR_SPLAT_SOFTMAX ? 1 : 2);
+    const bool pre = g.mode == FLDR_SPLAT_SOFTMAX;
+    if (n4 <= (long long)get_option(kOptSplatFusedMax) && get_option(kOptSplatFusedMax) > 0) {
         // small frame: single cooperative launch (zero / scatter / normalise separated by grid barriers)
-        const int wkind = !g.has_metric ? 0 : (g.mode == FLDR_SPLAT_SOFTMAX ? 1 : 2);
-        const bool pre = g.mode == FLDR_SPLAT_SOFTMAX;
         const void* fn = wkind == 1 ? (const void*)splat_fused_small_kernel<4, 1, true>
                        : wkind == 2 ? (const void*)splat_fused_small_kernel<4, 2, false>
                        : pre        ? (const void*)splat_fused_small_kernel<4, 0, true>
                                     : (const void*)splat_fused_small_kernel<4, 0, false>;
-        static int per_sm[4] = {0, 0, 0, 0};
+        static int per_sm[64][4];                      // occupancy per device and instantiation, computed once
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) dev = 0;
         const int slot = wkind == 1 ? 0 : wkind == 2 ? 1 : pre ? 2 : 3;
-        if (per_sm[slot] == 0) {
-            int nb = 0;
+        int nb = __atomic_load_n(&per_sm[dev][slot], __ATOMIC_ACQUIRE);
+        if (nb == 0) {
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, 256, 0) != cudaSuccess || nb < 1) nb = 1;
-            per_sm[slot] = nb;
+            __atomic_store_n(&per_sm[dev][slot], nb, __ATOMIC_RELEASE);
         }
         const long long units = (long long)N * Q * ((H + 3) / 4) * ((W + 31) / 32);     // warps wanted in phase B
         long long blocks = (units + 7) / 8;
         const long long blocks_c = (n4 + 255) / 256;
         if (blocks < blocks_c) blocks = blocks_c;
-        const long long cap = (long long)sm_count() * per_sm[slot];
+        const long long cap = (long long)sm_count() * nb;
         if (blocks > cap) blocks = cap;
         SplatGeom gg = g;
         int QQ = Q;
@@ -601,16 +751,40 @@ static int launch_whole_frame(const FwdPlan& p, const View4& vin, const View4& v
         if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
         return FLDR_OK;
     }
-    if (guard) {
-        long long blocks = (n4 + 255) / 256;
-        if (blocks > (long long)sm_count() * 8) blocks = (long long)sm_count() * 8;
-        splat_zero_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<float4*>(acc), n4, guard);
-        if ((st = check_launch()) != FLDR_OK) return st;
-    } else {
-        cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)n4 * 16, s);
+    {
+        cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)N * Q * H * (W + 2) * 16, s);
         if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
     }
-    {
+    // quad shape known at compile time for the image splat (C = 3 + weight) and for all-full-quad inputs
+    const int qs = (g.C == 3 && g.CA == 4) ? 1 : (g.CA == g.C && g.C % 4 == 0) ? 2 : 0;
+    // accumulators larger than ~half the L2 are DRAM-resident when the reductions arrive: prefetch their lines
+    const int pf_opt = get_option(kOptSplatPfRows);
+    const int pf = ((size_t)n4 * 16 > (48u << 20)) ? (pf_opt > 0 ? pf_opt : (pf_opt < 0 ? 0 : 4)) : 0;
+    bool tiled = get_option(kOptSplatStream) != 0 && view_tma_ok(vin) && view_tma_ok(vfl) && (!g.has_metric || (view_tma_ok(vme) && g.C < 4));
+    CUtensorMap tm_in, tm_fl, tm_me;
+    const int nbox = (Q == 1) ? g.C : 4;               // channels per input box
+    if (tiled) {
+        tiled = encode_view(&tm_in, vin, N, g.C, H, W, nbox) && encode_view(&tm_fl, vfl, N, 2, H, W, 2);
+        if (tiled && g.has_metric) tiled = encode_view(&tm_me, vme, N, 1, H, W, 1);
+        if (tiled && !g.has_metric) tm_me = tm_fl;
+    }
+    if (tiled) {
+        dim3 grid((W + tile::TW - 1) / tile::TW, (H + tile::R - 1) / tile::R, N * Q);
+#define FLDR_LAUNCH_TILE2(WK_, PRE_, QS_) \
+    splat_scatter_tile_kernel<WK_, PRE_, QS_><<<grid, tile::TW, 0, s>>>(tm_in, tm_fl, tm_me, acc, g, Q, nbox, pf)
+#define FLDR_LAUNCH_TILE(WK_, PRE_)                                       \
+    do {                                                                  \
+        if (qs == 1) FLDR_LAUNCH_TILE2(WK_, PRE_, 1);                     \
+        else if (qs == 2) FLDR_LAUNCH_TILE2(WK_, PRE_, 2);                \
+        else FLDR_LAUNCH_TILE2(WK_, PRE_, 0);                             \
+    } while (0)
+        if (wkind == 1) FLDR_LAUNCH_TILE(1, true);
+        else if (wkind == 2) FLDR_LAUNCH_TILE(2, false);
+        else if (pre) FLDR_LAUNCH_TILE(0, true);
+        else FLDR_LAUNCH_TILE(0, false);
+#undef FLDR_LAUNCH_TILE2
+#undef FLDR_LAUNCH_TILE
+    } else {
         // rows walked per thread: 16 merges best vertically, but the walk is serial - shorten it until the grid offers
         // at least two waves of CTAs (8 x 128 threads per SM)
         const int bx = W >= 128 ? 128 : ((W + 31) / 32) * 32;
@@ -619,15 +793,8 @@ static int launch_whole_frame(const FwdPlan& p, const View4& vin, const View4& v
         int R = 16;
         while (R > 4 && per_row_ctas * ((H + R - 1) / R) < two_waves) R >>= 1;
         dim3 grid((W + bx - 1) / bx, (H + R - 1) / R, N * Q);
-        const int wkind = !g.has_metric ? 0 : (g.mode == FLDR_SPLAT_SOFTMAX ? 1 : 2);
-        const bool pre = g.mode == FLDR_SPLAT_SOFTMAX;
-        // quad shape known at compile time for the image splat (C = 3 + weight) and for all-full-quad inputs
-        const int qs = (g.C == 3 && g.CA == 4) ? 1 : (g.CA == g.C && g.C % 4 == 0) ? 2 : 0;
-        // accumulators larger than ~half the L2 are DRAM-resident when the reductions arrive: prefetch their lines
-        const int pf_opt = get_option(kOptSplatPfRows);
-        const int pf = ((size_t)n4 * 16 > (48u << 20)) ? (pf_opt > 0 ? pf_opt : (pf_opt < 0 ? 0 : 4)) : 0;
 #define FLDR_LAUNCH_SCATTER2(WK_, PRE_, QS_) \
-    splat_scatter_merged_kernel<WK_, PRE_, QS_><<<grid, bx, 0, s>>>(vin, vfl, vme, acc, g, Q, guard, pf, R)
+    splat_scatter_merged_kernel<WK_, PRE_, QS_><<<grid, bx, 0, s>>>(vin, vfl, vme, acc, g, Q, pf, R)
 #define FLDR_LAUNCH_SCATTER(WK_, PRE_)                                       \
     do {                                                                     \
         if (qs == 1) FLDR_LAUNCH_SCATTER2(WK_, PRE_, 1);                     \
@@ -642,36 +809,7 @@ static int launch_whole_frame(const FwdPlan& p, const View4& vin, const View4& v
 #undef FLDR_LAUNCH_SCATTER
     }
     if ((st = check_launch()) != FLDR_OK) return st;
-    return launch_normalise(p, acc, out, norm, guard, s);
-}
-
-// which path serves a call: 0 = single cooperative launch (tiny frames), 1 = whole-frame three-pass, 2 = ring kernel
-static int pick_path(const FwdPlan& p, const View4& vin, const View4& vfl, const View4& vme, const float* out, const float* norm) {
-    const long long n4 = (long long)p.g.N * p.Q * p.g.H * p.g.W;
-    if (get_option(kOptSplatFusedMax) > 0 && n4 <= (long long)get_option(kOptSplatFusedMax)) return 0;
-    if (get_option(kOptSplatStream) != 0 && p.ring.ok && ring_eligible(p.g, vin, vfl, vme, out, norm)) return 2;
-    return 1;
-}
-
-extern "C" int fldr_splat_fwd_plan(int mode, int N, int C, int H, int W, int has_metric, int64_t* info) {
-    FwdPlan p;
-    int st = plan_fwd(mode, N, C, H, W, has_metric != 0, p);
-    if (st != FLDR_OK) return st;
-    if (!info) return FLDR_ERR_INVALID_ARGUMENT;
-    // path for dense, aligned NCHW tensors
-    View4 v;
-    v.p = nullptr; v.sw = 1; v.sh = W; v.sc = (long long)H * W; v.sn = (long long)C * H * W;
-    View4 v2 = v; v2.sn = 2ll * H * W;
-    View4 v1 = v; v1.sn = (long long)H * W;
-    info[0] = pick_path(p, v, v2, v1, nullptr, nullptr);
-    info[1] = p.ring.ok ? (p.ring.rg.bounded ? (int64_t)p.ring.rg.Ds * 8 : -1) : 0;     // vertical reach in rows, -1 = unbounded
-    info[2] = p.ring.ok ? (int64_t)p.ring.ring_bytes : 0;
-    info[3] = (int64_t)(p.ring_bytes + (size_t)kRingCtrlFlag * 4);                       // byte offset of the flag word in ws
-    info[4] = p.ring.ok ? p.ring.rg.ring_rows : 0;
-    info[5] = p.ring.ok ? p.ring.rg.total : 0;
-    info[6] = (int64_t)p.total_bytes;
-    info[7] = 0;
-    return FLDR_OK;
+    return launch_normalise(p, acc, out, norm, s);
 }
 
 extern "C" int fldr_splat_fwd(int mode, const float* in, const int64_t* in_strides, const float* flow,
@@ -682,24 +820,12 @@ extern "C" int fldr_splat_fwd(int mode, const float* in, const int64_t* in_strid
     int st = plan_fwd(mode, N, C, H, W, metric != nullptr, p);
     if (st != FLDR_OK) return st;
     if (!in || !in_strides || !flow || !flow_strides || !out || (metric && !metric_strides)) return FLDR_ERR_INVALID_ARGUMENT;
-    if (!ws || ws_bytes < p.total_bytes) return FLDR_ERR_WORKSPACE_TOO_SMALL;
+    if (!ws || ws_bytes < p.acc_bytes) return FLDR_ERR_WORKSPACE_TOO_SMALL;
     if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return FLDR_ERR_INVALID_ARGUMENT;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const View4 vin = make_view(in, in_strides), vfl = make_view(flow, flow_strides), vme = make_view(metric, metric_strides);
-    char* base = static_cast<char*>(ws);
-    void* ring = base;
-    unsigned* ctrl = reinterpret_cast<unsigned*>(base + p.ring_bytes);
-    float* full = reinterpret_cast<float*>(base + p.ring_bytes + p.ctrl_bytes);
     if (!mode_has_norm(mode)) norm = nullptr;
-
-    if (pick_path(p, vin, vfl, vme, out, norm) != 2) return launch_whole_frame(p, vin, vfl, vme, full, out, norm, nullptr, s);
-
-    st = launch_ring(p.ring, p.g, vin, vfl, vme, ring, ctrl, out, norm, s);
-    if (st == FLDR_ERR_UNSUPPORTED) return launch_whole_frame(p, vin, vfl, vme, full, out, norm, nullptr, s);   // no tensor map for these views
-    if (st != FLDR_OK) return st;
-    // bounded reach: arm the whole-frame path; its launches exit at once unless the ring kernel raised the flag
-    if (p.ring.rg.bounded) return launch_whole_frame(p, vin, vfl, vme, full, out, norm, ctrl + kRingCtrlFlag, s);
-    return FLDR_OK;
+    return launch_forward(p, vin, vfl, vme, static_cast<float*>(ws), out, norm, s);
 }
 
 extern "C" size_t fldr_splat_bwd_workspace_bytes(int mode, int N, int C, int H, int W) {

@@ -33,38 +33,4 @@ __device__ __forceinline__ float post_scale(float sv, float d, bool raw, bool ha
     return (sv * d - 0.5f) * 2.f;
 }
 
-// ---- ring path (splat_ring.cu) ----
-struct RingGeom {
-    int NS;          // strips per sample = ceil(H / 8)
-    int NT;          // N * NS absolute strips
-    int T;           // column tiles = ceil(W / 128)
-    int Q;           // channel quads
-    int RS;          // ring strips
-    int Ds;          // vertical reach in strips
-    int pitch;       // ring row pitch in float4 cells = W + 2 (one guard cell either side: no x test on the reductions)
-    int ring_rows;   // RS * 8
-    int mask;        // ring_rows - 1 (bounded: a power of two) or all ones (the ring holds the whole batch: no wrap)
-    int nZs, nZ;     // ring slots zeroed up front = min(RS, NT), and the zero-fill items that takes (nZs * T)
-    int TQ;          // T * Q scatter items per strip (T normalise items per strip)
-    int total;       // all work items
-    int bounded;     // ring smaller than the batch: reach is bounded, the whole-frame fallback must be armed
-    int spin_limit;  // watchdog of the dependency polls
-};
-
-struct RingPlan {
-    RingGeom rg;
-    bool ok;
-    size_t ring_bytes, ctrl_bytes;
-};
-
-constexpr int kRingCtrlClaim = 0;      // ctrl word indices (unsigned): {N tickets claimed, S tickets claimed, scatter frontier, clean frontier}
-constexpr int kRingCtrlFlag = 32;      // bit 0: a source left the ring's reach, bit 1: watchdog
-constexpr int kRingCtrlCounters = 64;  // sdone[NT], then ev[nZs + NT]
-
-// Can the ring kernel serve this call?  (layout / alignment requirements of its bulk copies and vector stores)
-bool ring_eligible(const SplatGeom& g, const View4& in, const View4& flow, const View4& metric, const float* out, const float* norm);
-void plan_ring(const SplatGeom& g, RingPlan& p);
-int launch_ring(const RingPlan& p, const SplatGeom& g, const View4& in, const View4& flow, const View4& metric, void* ring,
-                unsigned* ctrl, float* out, float* norm, cudaStream_t s);
-
 }  // namespace fldr

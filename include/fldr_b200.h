@@ -65,16 +65,12 @@ const char* fldr_status_string(int status);
 int fldr_last_cuda_error(void);
 /*
  * Tuning / diagnostic switches (process-wide; initial values come from FLDR_<NAME> environment variables):
- *   "splat_stream"   1 (default): frames too large for the single cooperative launch run the streaming kernel (one
- *                    launch, L2-resident ring accumulator) when their layout allows it; 0 = always the
- *                    whole-frame three-pass path
- *   "splat_ring_mb"  ring size cap of the streaming kernel in MiB (0 = 34, at most 72)
- *   "splat_lag"      schedule lag of the streaming kernel in strips of 8 rows (0 = automatic)
+ *   "splat_tma"      1 (default): the scatter pass stages its inputs with TMA box loads when the views allow it
+ *                    (16-byte aligned rows, unit pixel stride); 0 = always the plain-load scatter kernel
  *   "splat_fused_max" frames with at most this many accumulator float4s (N * ceil((C+1)/4) * H * W, default 40000)
  *                    run zero + scatter + normalise as ONE cooperative launch; 0 disables
  *   "corr_th"        tile height of the correlation forward kernel: 0 automatic, 8 or 16 forced
- *   "splat_pf_rows"  whole-frame path: accumulator rows prefetched into L2 ahead of the scatter (0 = default 4,
- *                    negative = off)
+ *   "splat_pf_rows"  accumulator rows prefetched into L2 ahead of the scatter (0 = default 4, negative = off)
  * Results are identical (within the summation-order tolerance) for every setting.
  */
 int fldr_set_option(const char* name, int value);
@@ -95,17 +91,6 @@ size_t fldr_splat_fwd_workspace_bytes(int mode, int N, int C, int H, int W);
  *                      fldr_splat_bwd.  Ignored (may be NULL) for SUMMATION / RAW.
  * Pixels whose target coordinate is not finite are skipped (the reference device-asserts, 25-26).
  */
-/*
- * Diagnostic: how fldr_splat_fwd will serve this shape (for dense, 16-byte-aligned NCHW tensors; has_metric: a
- * metric tensor is passed).  info[8]:
- *   [0] path: 0 single cooperative launch, 1 whole-frame three-pass, 2 streaming ring kernel
- *   [1] vertical reach of the ring kernel in rows (-1 unbounded, 0 ring path unavailable); a flow beyond it is
- *       handled by the guarded whole-frame launches that follow the ring kernel (same results, no host sync)
- *   [2] ring bytes  [3] byte offset inside `ws` of the flag word the ring kernel raises (bit 0: reach exceeded,
- *       bit 1: dependency watchdog)  [4] ring rows  [5] work items  [6] workspace bytes  [7] reserved
- */
-int fldr_splat_fwd_plan(int mode, int N, int C, int H, int W, int has_metric, int64_t* info);
-
 int fldr_splat_fwd(int mode,
                    const float* in, const int64_t* in_strides,
                    const float* flow, const int64_t* flow_strides,

@@ -46,7 +46,7 @@ def test_status_strings_and_version(lib):
 
 def test_options_roundtrip(lib):
     """fldr_set_option / fldr_get_option: every documented switch exists, unknown names are rejected."""
-    for name in (b"splat_stream", b"splat_ring_mb", b"splat_lag", b"splat_fused_max", b"corr_th", b"splat_pf_rows"):
+    for name in (b"splat_tma", b"splat_fused_max", b"corr_th", b"splat_pf_rows"):
         old = lib.fldr_get_option(name)
         assert lib.fldr_set_option(name, 7) == 0 and lib.fldr_get_option(name) == 7
         assert lib.fldr_set_option(name, old) == 0
@@ -56,40 +56,21 @@ def test_options_roundtrip(lib):
 
 
 def test_workspace_sizes(lib):
-    # 4K image splat: ring region (sized for the largest ring "splat_ring_mb" may select: 1024 rows of W + 2 cells; the
-    # default ring uses 512 of them) + control words + whole-frame accumulator for the fallback
-    ring = 1024 * 4098 * 16
-    full = 2304 * 4096 * 16
+    # 4K image splat: the accumulator, rows of W + 2 float4 cells (one guard cell either side)
+    acc = 2304 * 4098 * 16
     ws = lib.fldr_splat_fwd_workspace_bytes(3, 1, 3, 2304, 4096)
-    assert ring + full <= ws <= ring + full + (1 << 16)
-    # feature splat level 0: the ring holds the whole frame (13 quads x 288 rows): unbounded reach
+    assert acc <= ws <= acc + 256
+    # feature splat level 0: 13 channel quads
     ws = lib.fldr_splat_fwd_workspace_bytes(3, 1, 48, 288, 512)
-    lo = 13 * 288 * 514 * 16 + 13 * 288 * 512 * 16
-    assert lo <= ws <= lo + (1 << 16)
+    assert 13 * 288 * 514 * 16 <= ws <= 13 * 288 * 514 * 16 + 256
     assert lib.fldr_splat_fwd_workspace_bytes(9, 1, 3, 8, 8) == 0          # unknown mode
     # the size depends on the shape only: tuning options must not change it (a size cached per shape stays valid)
     ws0 = lib.fldr_splat_fwd_workspace_bytes(3, 1, 3, 2304, 4096)
-    for name, val in ((b"splat_ring_mb", 16), (b"splat_ring_mb", 64), (b"splat_lag", 20), (b"splat_stream", 0)):
+    for name, val in ((b"splat_tma", 0), (b"splat_fused_max", 0), (b"splat_pf_rows", 8)):
         old = lib.fldr_get_option(name)
         lib.fldr_set_option(name, val)
         assert lib.fldr_splat_fwd_workspace_bytes(3, 1, 3, 2304, 4096) == ws0
         lib.fldr_set_option(name, old)
-
-
-def test_splat_plan(lib):
-    """fldr_splat_fwd_plan: which path serves a shape and the ring kernel's vertical reach."""
-    import ctypes
-    info = (ctypes.c_int64 * 8)()
-    assert lib.fldr_splat_fwd_plan(3, 1, 3, 2304, 4096, 1, info) == 0
-    assert info[0] == 2 and info[4] == 512 and 64 <= info[1] <= 256       # bounded ring, reach in rows
-    assert info[6] == lib.fldr_splat_fwd_workspace_bytes(3, 1, 3, 2304, 4096)
-    assert lib.fldr_splat_fwd_plan(3, 1, 48, 288, 512, 0, info) == 0
-    assert info[0] == 2 and info[1] == -1                                  # whole batch inside the ring
-    assert lib.fldr_splat_fwd_plan(3, 1, 48, 18, 32, 0, info) == 0
-    assert info[0] == 0                                                    # tiny frame: single cooperative launch
-    assert lib.fldr_splat_fwd_plan(3, 1, 3, 300, 1026, 1, info) == 0
-    assert info[0] == 1                                                    # W % 4 != 0: whole-frame path
-    assert lib.fldr_splat_fwd_plan(9, 1, 3, 8, 8, 0, info) != 0
 
 
 def test_argument_validation_needs_no_device(lib):

@@ -212,27 +212,10 @@ def test_feature_splat_L0_vs_oracle_full(cuda_lib):
     assert_splat_close(gi, gio, "feature L0 grad_input")
 
 
-def _raw_call(lib, x, fl, z, mode=3):
-    """fldr_splat_fwd through the C ABI with a workspace the test owns; returns (out, path, reach rows, flag word)."""
-    import ctypes
-    import fldr_vfi_b200._lib as L
-    N, C, H, W = x.shape
-    info = (ctypes.c_int64 * 8)()
-    assert lib.fldr_splat_fwd_plan(mode, N, C, H, W, int(z is not None), info) == 0
-    ws = torch.zeros(int(info[6]), dtype=torch.uint8, device="cuda")
-    out = torch.empty_like(x)
-    st = lib.fldr_splat_fwd(mode, L.ptr(x), L.strides(x), L.ptr(fl), L.strides(fl), L.ptr(z), None if z is None else L.strides(z),
-                            L.ptr(out), None, N, C, H, W, L.ptr(ws), int(info[6]),
-                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-    L.check(st)
-    torch.cuda.synchronize()
-    flag = int(ws[int(info[3]):int(info[3]) + 4].view(torch.int32)[0]) if info[0] == 2 else -1
-    return out, int(info[0]), int(info[1]), flag
-
-
 @pytest.fixture
-def ring_everywhere(cuda_lib):
-    """Send small frames through the streaming kernel too (they normally take the single cooperative launch)."""
+def tile_everywhere(cuda_lib):
+    """Send small frames through the three-pass path with the TMA tile scatter kernel too (they normally take the single
+    cooperative launch)."""
     old = cuda_lib.fldr_get_option(b"splat_fused_max")
     cuda_lib.fldr_set_option(b"splat_fused_max", 0)
     yield
@@ -240,65 +223,63 @@ def ring_everywhere(cuda_lib):
 
 
 @pytest.fixture
-def whole_frame(cuda_lib):
-    """Switch the streaming kernel off: the whole-frame three-pass path serves the call."""
-    cuda_lib.fldr_set_option(b"splat_stream", 0)
+def plain_loads(cuda_lib):
+    """Switch the TMA staging off: the plain-load scatter kernel (what odd views take) serves the call."""
+    cuda_lib.fldr_set_option(b"splat_tma", 0)
     yield
-    cuda_lib.fldr_set_option(b"splat_stream", 1)
+    cuda_lib.fldr_set_option(b"splat_tma", 1)
 
 
 @pytest.mark.parametrize("shape,regime,with_metric", [
     ((1, 3, 256, 448), "F1", True), ((1, 48, 32, 56), "F2", False), ((2, 5, 36, 48), "FB", False), ((3, 7, 8, 132), "F2", False),
-    ((2, 3, 64, 96), "F3", True), ((1, 3, 4, 4), "F0", True), ((2, 3, 40, 260), "FB", True),
+    ((2, 3, 64, 96), "F3", True), ((1, 3, 4, 4), "F0", True), ((2, 3, 40, 260), "FB", True), ((1, 16, 37, 68), "F2", False),
 ])
-def test_ring_kernel_small_frames(cuda_lib, ring_everywhere, shape, regime, with_metric):
-    """Every quad shape / metric kind / ragged tile of the streaming kernel against the oracle; the ring holds the whole
-    batch here, so nothing may raise the flag word."""
+def test_tile_kernel_small_frames(cuda_lib, tile_everywhere, shape, regime, with_metric):
+    """Every quad shape / metric kind / ragged tile of the TMA tile scatter kernel against the oracle."""
+    S = _mods(cuda_lib)
     N, C, H, W = shape
     x = synth.features(N, C, H, W, seed=11)
     fl = synth.flow(N, H, W, regime, seed=12)
     z = synth.metric(N, H, W, seed=13) if with_metric else None
-    y, path, reach, flag = _raw_call(cuda_lib, x.cuda(), fl.cuda(), None if z is None else z.cuda())
-    assert path == 2 and reach == -1 and flag == 0
-    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "ring small", mag=1.0)
+    y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), None if z is None else z.cuda(), "softmax")
+    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "tile small", mag=1.0)
 
 
-@pytest.mark.parametrize("mode", ["summation", "average", "linear", "raw"])
-def test_ring_kernel_other_modes(cuda_lib, ring_everywhere, mode):
-    import fldr_vfi_b200._lib as L
+@pytest.mark.parametrize("mode", ["summation", "average", "linear"])
+def test_tile_kernel_other_modes(cuda_lib, tile_everywhere, mode):
+    S = _mods(cuda_lib)
     N, C, H, W = 2, 6 if mode != "linear" else 3, 40, 64
     x = synth.features(N, C, H, W, seed=21)
     fl = synth.flow(N, H, W, "F2", seed=22)
     z = synth.metric(N, H, W, seed=23) if mode == "linear" else None
-    ref = so.splat_raw(x, fl) if mode == "raw" else so.function_softsplat(x, fl, z, mode)
-    y, path, _, flag = _raw_call(cuda_lib, x.cuda(), fl.cuda(), None if z is None else z.cuda(), L.SPLAT_MODES[mode])
-    assert path == 2 and flag == 0
-    assert_splat_close(y, ref, "ring " + mode)
+    y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), None if z is None else z.cuda(), mode)
+    assert_splat_close(y, so.function_softsplat(x, fl, z, mode), "tile " + mode)
+    raw = S._FunctionSoftsplat.apply(x.cuda(), fl.cuda())
+    assert_splat_close(raw, so.splat_raw(x, fl), "tile raw")
 
 
-def test_whole_frame_path_4k(cuda_lib, whole_frame):
-    """The three-pass path (what the fallback and unaligned views run) at the 4K size."""
+def test_plain_load_path_4k(cuda_lib, plain_loads):
+    """The plain-load scatter kernel (odd views) at the 4K size."""
     S = _mods(cuda_lib)
     x = synth.image(1, 3, H4K, W4K, seed=56)
     fl = synth.flow(1, H4K, W4K, "F1", seed=57)
     z = synth.metric(1, H4K, W4K, seed=58)
     y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), z.cuda(), "softmax")
-    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "4K whole-frame", mag=1.0)
+    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "4K plain loads", mag=1.0)
 
 
-def test_ring_kernel_4k_stays_on_ring(cuda_lib):
-    """The headline flow regimes F1 / F2 fit the 4K ring's vertical reach: the flag word stays 0 (no fallback ran)."""
-    x = synth.image(1, 3, H4K, W4K, seed=56).cuda()
-    z = synth.metric(1, H4K, W4K, seed=58).cuda()
-    for regime, seed in (("F1", 57), ("F2", 59)):
-        fl = synth.flow(1, H4K, W4K, regime, seed=seed)
-        y, path, reach, flag = _raw_call(cuda_lib, x, fl.cuda(), z)
-        assert path == 2 and reach >= 64 and flag == 0, (regime, path, reach, flag)
-        assert float(fl[:, 1].abs().max()) < reach
+def test_4k_converge_regime_vs_oracle(cuda_lib):
+    """Flow regime F3 (every pixel flows to the frame centre: maximum contention) at the full 4K size."""
+    S = _mods(cuda_lib)
+    x = synth.image(1, 3, H4K, W4K, seed=56)
+    fl = synth.flow(1, H4K, W4K, "F3", seed=60)
+    z = synth.metric(1, H4K, W4K, seed=58)
+    y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), z.cuda(), "softmax")
+    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "4K softmax F3", mag=1.0)
 
 
-def test_unaligned_views_take_whole_frame_path(cuda_lib):
-    """Views the bulk copies cannot take (odd width, column-sliced rows) are served by the whole-frame path."""
+def test_unaligned_views_take_plain_load_path(cuda_lib):
+    """Views the TMA boxes cannot take (odd width, column-sliced rows, metric with >= 4 channels) run the plain-load kernel."""
     S = _mods(cuda_lib)
     N, H, W = 1, 300, 1027
     x = synth.image(N, 3, H, W, seed=61)
@@ -310,33 +291,15 @@ def test_unaligned_views_take_whole_frame_path(cuda_lib):
     fs, zs = fl.cuda()[:, :, :, 3:1027], z.cuda()[:, :, :, 3:1027]
     y = S.FunctionSoftsplat(xs, fs, zs, "softmax")
     assert_splat_close(y, so.function_softsplat(x[:, :, :, 3:1027], fl[:, :, :, 3:1027], z[:, :, :, 3:1027], "softmax"), "sliced rows", mag=1.0)
+    x6 = synth.features(2, 6, 200, 256, seed=64)
+    f6 = synth.flow(2, 200, 256, "F1", seed=65) * 4
+    z6 = synth.metric(2, 200, 256, seed=66)
+    y = S.FunctionSoftsplat(x6.cuda(), f6.cuda(), z6.cuda(), "softmax")
+    assert_splat_close(y, so.function_softsplat(x6, f6, z6, "softmax"), "metric with 6 channels", mag=1.0)
 
 
-def test_bounded_ring_overflow_falls_back(cuda_lib):
-    """Frames taller than the L2-resident ring bound the vertical reach of the streaming kernel; a flow beyond it must
-    raise the flag on the device and the guarded whole-frame launches re-do the call (no host sync) - same result."""
-    S = _mods(cuda_lib)
-    H, W = 1152, 4096                      # ring for W=4096 holds 512 rows
-    x = synth.image(1, 3, H, W, seed=81)
-    z = synth.metric(1, H, W, seed=82)
-    fl = synth.flow(1, H, W, "F1", seed=83)
-    fl[:, 1, 300:340, 1000:1400] += 260.0      # a block moving 260 rows down: beyond the reach
-    fl[:, 1, 900:930, 2000:2100] -= 400.0      # and one moving 400 rows up
-    ref = so.function_softsplat(x, fl, z, "softmax")
-    y, path, reach, flag = _raw_call(cuda_lib, x.cuda(), fl.cuda(), z.cuda())
-    assert path == 2 and 0 < reach < 260 and flag == 1
-    assert_splat_close(y, ref, "overflow fallback", mag=1.0)
-    assert_splat_close(S.FunctionSoftsplat(x.cuda(), fl.cuda(), z.cuda(), "softmax"), ref, "overflow fallback (wrapper)", mag=1.0)
-    # and the in-reach case on the same shape (pure streaming path) for contrast
-    fl2 = synth.flow(1, H, W, "F1", seed=84)
-    fl2[:, 1, 300:340, 1000:1400] += 60.0
-    y2, _, _, flag2 = _raw_call(cuda_lib, x.cuda(), fl2.cuda(), z.cuda())
-    assert flag2 == 0
-    assert_splat_close(y2, so.function_softsplat(x, fl2, z, "softmax"), "in-reach streaming", mag=1.0)
-
-
-def test_batched_tall_frames_ring(cuda_lib):
-    """N > 1 with a ring smaller than the batch: strips of consecutive samples share ring slots across epochs."""
+def test_batched_tall_frames(cuda_lib):
+    """N > 1 tall frames, forward and all gradients."""
     S = _mods(cuda_lib)
     N, H, W = 3, 640, 4096
     x = synth.image(N, 3, H, W, seed=91)
@@ -353,8 +316,6 @@ def test_batched_tall_frames_ring(cuda_lib):
     assert_splat_close(grads[0], gi, "batched tall grad_input", cond=gi - gi64)
     assert_splat_close(grads[1], gf, "batched tall grad_flow", cond=gf - gf64)
     assert_splat_close(grads[2], gz, "batched tall grad_metric", cond=gz - gz64)
-    _, path, _, flag = _raw_call(cuda_lib, x.cuda(), fl.cuda(), z.cuda())
-    assert path == 2 and flag == 0
 
 
 def test_cfg5_training_shapes_vs_oracle(cuda_lib):
