@@ -117,6 +117,34 @@ def worker(impl, out_path, reps, height, width):
     print(json.dumps({"impl": impl, "psnr": psnr, "median_s": sorted(times)[len(times) // 2], "softSplat": which}))
 
 
+def compact(a):
+    """bench.py's leg: the listed variants, median / min / max of the model forward, PSNR per variant, ratios to the reference."""
+    import torch
+    res = {}
+    for tag in a.variants.split(","):
+        out = f"/tmp/fldr_e2e_{tag}.pt"
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", tag, "--out", out, "--reps", str(a.reps),
+                            "--height", str(a.height), "--width", str(a.width)], capture_output=True, text=True)
+        if r.returncode != 0:
+            print(json.dumps({"unavailable": f"{tag} failed: " + r.stderr[-400:]}))
+            return
+        res[tag] = torch.load(out, weights_only=False)
+    rep = {"frame": f"{a.width}x{a.height}", "reps": a.reps, "variants": {}}
+    for tag, v in res.items():
+        ts = sorted(v["times"])
+        rep["variants"][tag] = {"forward_s_median": ts[len(ts) // 2], "forward_s_min": ts[0], "forward_s_max": ts[-1],
+                                "frame_pairs_per_s": 1.0 / ts[len(ts) // 2], "psnr_dB": v["psnr"], "ops": v["softSplat"].split("/")[-1]}
+    if "reference" in res:
+        ref = rep["variants"]["reference"]
+        for tag, v in rep["variants"].items():
+            if tag != "reference":
+                v["speedup_vs_reference_median"] = ref["forward_s_median"] / v["forward_s_median"]
+                v["speedup_vs_reference_worst_case"] = ref["forward_s_min"] / v["forward_s_max"]
+                v["psnr_abs_diff_dB"] = abs(v["psnr_dB"] - ref["psnr_dB"])
+                v["max_abs_output_diff"] = float((res[tag]["pred"] - res["reference"]["pred"]).abs().max())
+    print(json.dumps(rep))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--impl", default=None, choices=["ours", "ours_warp", "ours_warp_keepcache", "reference"])
@@ -124,11 +152,15 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--width", type=int, default=4096)
+    ap.add_argument("--variants", default=None, help="comma list of reference,ours,ours_warp,ours_warp_keepcache: compact report")
     a = ap.parse_args()
     if a.impl:
         worker(a.impl, a.out, a.reps, a.height, a.width)
         return
     import torch
+    if a.variants:
+        compact(a)
+        return
     res = {}
     for tag in ("reference", "reference_again", "ours", "ours_warp", "ours_warp_keepcache"):
         impl = "reference" if tag.startswith("reference") else tag

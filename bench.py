@@ -45,6 +45,16 @@ def corr_flops(B, C, H, W):
     return 162 * C * B * H * W
 
 
+def shared_config():
+    """`config` of the JSON line - the SAME dict in the `ours` and `reference` arms (arm-specific notes go in `notes`)."""
+    return {"workload": "one 4K frame pair per step per GPU: 12 softmax splats of fLDRnet --papermodel --test5scales "
+                        "(2x image C=3+metric 2304x4096, 2x feature C=48 at 5 levels) + 5-level PWC correlation "
+                        "pyramid at native 4K (B=2, C=196..32)",
+            "flow_regime": "F1 smooth",
+            "algorithmic_MB_per_step": 1820.2,
+            "sharding": "frame pairs across ranks, no collective"}
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -56,11 +66,13 @@ def measured_peak_gbs():
 
 
 def ncu_traffic(call):
-    """DRAM bytes per call of `call` from the committed ncu --set full capture (profiles/r1_traffic.json), or None."""
-    try:
-        return int(json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[call]["bytes"])
-    except Exception:
-        return None
+    """DRAM bytes per call of `call` from the committed ncu --set full capture (profiles/r2_traffic.json, else r1), or None."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            return int(json.load(open(os.path.join(ROOT, "profiles", name)))[call]["bytes"])
+        except Exception:
+            continue
+    return None
 
 
 # ----------------------------------------------------------------------------------------------- inputs
@@ -146,9 +158,48 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+def pin_rank_to_cores(local_rank, world):
+    """Give every rank its own slice of the host cores nearest its GPU (NVML affinity mask), so the pinned staging buffers
+    it allocates afterwards are first-touched - and the copy engines are fed - from that NUMA node.  Returns the cores."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local_rank]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        near = [i for i in range(os.cpu_count()) if (words[i // 64] >> (i % 64)) & 1]
+    except Exception:
+        near = []
+    allowed = sorted(os.sched_getaffinity(0))
+    near = [c for c in near if c in allowed] or allowed
+    per = max(1, len(near) // max(world, 1))
+    mine = near[(local_rank * per) % len(near):][:per] or near
+    try:
+        os.sched_setaffinity(0, mine)
+        torch.set_num_threads(max(1, min(len(mine), 8)))
+    except Exception:
+        pass
+    return mine
+
+
+def median_event_ms(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0], ts[-1]
+
+
 # ----------------------------------------------------------------------------------------------- our arm
 def run_ours(args, rank, world, local_rank):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    cores = pin_rank_to_cores(local_rank, world)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
@@ -262,6 +313,15 @@ def run_ours(args, rank, world, local_rank):
         e1.record()
         barrier()
         ms_total = e0.elapsed_time(e1)
+        # the same K steps with eager launches on one stream (what a caller that does not capture graphs gets)
+        barrier()
+        e0.record()
+        for s in range(args.steps):
+            for n, t in devin:
+                run_call(n, t)
+        e1.record()
+        barrier()
+        ms_eager_total = e0.elapsed_time(e1)
 
         # ---------------- end to end: pinned host -> device -> ops -> pinned host, EVERY step, through the drop-in API.
         # Three streams (H2D / compute / D2H) and two buffer sets, so step k+1's upload and step k-1's download overlap
@@ -309,14 +369,108 @@ def run_ours(args, rank, world, local_rank):
             e2e_step(k)
         barrier()
         e2e_s = time.perf_counter() - t0
-        clk = clocks.stop()
         d2h_bytes = sum(o.numel() * 4 for o in out_sets[0])
 
+        # ---------------- e2e_frames: what a real pipeline moves over PCIe - the two frames up, the two warped frames down;
+        # flows, metrics, features and cost volumes are produced and consumed on the device (fLDRnet.py:368-453).  Same
+        # three-stream scheme; every step uploads both frames and downloads both splatted frames.
+        img_idx = [i for i, (n, _) in enumerate(pinned) if n == "splat_image"]
+        fr_dev = [[torch.empty_like(pinned[i][1]["x"], device=dev) for i in img_idx] for _ in range(2)]
+        fr_out = [[torch.empty(pinned[i][1]["x"].shape, dtype=torch.float32).pin_memory() for i in img_idx] for _ in range(2)]
+        fused = [False, False]
+
+        def frames_step(k):
+            b = k & 1
+            with torch.cuda.stream(s_in):
+                if fused[b]:
+                    s_in.wait_event(ev_comp[b])
+                for j, i in enumerate(img_idx):
+                    fr_dev[b][j].copy_(pinned[i][1]["x"], non_blocking=True)
+                ev_in[b].record(s_in)
+            s_comp.wait_event(ev_in[b])
+            outs = []
+            j = 0
+            for i, (n, t) in enumerate(devin):
+                if n == "splat_image":
+                    outs.append(splat(fr_dev[b][j], t["flow"], t["z"]))
+                    j += 1
+                else:
+                    run_call(n, t)
+            ev_comp[b].record(s_comp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_comp[b])
+                for oh, o in zip(fr_out[b], outs):
+                    o.record_stream(s_out)
+                    oh.copy_(o, non_blocking=True)
+                ev_out[b].record(s_out)
+            fused[b] = True
+
+        for k in range(2):
+            frames_step(k)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            frames_step(k)
+        barrier()
+        e2e_frames_s = time.perf_counter() - t0
+        frames_bytes = sum(pinned[i][1]["x"].numel() * 4 for i in img_idx)
+
+        # measured host <-> device copy ceiling of this rank (256 MiB pinned buffer, one direction at a time and both at once)
+        cbuf_h = torch.empty(64 << 20, dtype=torch.float32).pin_memory()
+        cbuf_h2 = torch.empty(64 << 20, dtype=torch.float32).pin_memory()
+        cbuf_d, cbuf_d2 = torch.empty(64 << 20, dtype=torch.float32, device=dev), torch.empty(64 << 20, dtype=torch.float32, device=dev)
+
+        def wall(fn, reps=4):
+            fn(); torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / reps
+
+        def both_ways():
+            with torch.cuda.stream(s_in):
+                cbuf_d.copy_(cbuf_h, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                cbuf_h2.copy_(cbuf_d2, non_blocking=True)
+        t_h2d = wall(lambda: cbuf_d.copy_(cbuf_h, non_blocking=True))
+        t_d2h = wall(lambda: cbuf_h2.copy_(cbuf_d2, non_blocking=True))
+        t_both = wall(both_ways)
+        nb = cbuf_h.numel() * 4
+        copy_ceiling = {"h2d_GBps": nb / t_h2d / 1e9, "d2h_GBps": nb / t_d2h / 1e9, "both_directions_GBps_each": nb / t_both / 1e9}
+        del cbuf_h, cbuf_h2, cbuf_d, cbuf_d2
+
+        # ---------------- strong scaling (BASELINE configs[3]): 64 DISTINCT frame pairs sharded by pair over the ranks
+        # (fldr_vfi_b200.sharding.run_sharded: pair i -> rank i mod N, no collective).  Pair i's inputs are this rank's
+        # tensors rolled by 8 i columns (built on the device, outside the timed events); each pair's step is timed with
+        # CUDA events; a rank's time is the sum over its pairs, the job's time the max over ranks.
+        from fldr_vfi_b200 import sharding
+        n_pairs = 64
+
+        def run_pair(i):
+            inputs = [(n, {k: (None if v is None else torch.roll(v, shifts=8 * i, dims=-1)) for k, v in t.items()}) for n, t in devin]
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for n, t in inputs:
+                run_call(n, t)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b)
+        barrier()
+        pair_ms = sharding.run_sharded(list(range(n_pairs)), run_pair, rank, world)
+        strong_ms = sum(pair_ms.values())
+        clk = clocks.stop()
+
     # max over ranks
+    copy_min = dict(copy_ceiling)
     if world > 1:
-        tt = torch.tensor([ms_total, e2e_s], device=dev, dtype=torch.float64)
+        tt = torch.tensor([ms_total, e2e_s, ms_eager_total, e2e_frames_s, strong_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s = float(tt[0]), float(tt[1])
+        ms_total, e2e_s, ms_eager_total, e2e_frames_s, strong_ms = (float(v) for v in tt)
+        cc = torch.tensor([copy_ceiling["h2d_GBps"], copy_ceiling["d2h_GBps"], copy_ceiling["both_directions_GBps_each"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(cc, op=dist.ReduceOp.MIN)
+        copy_min = {"h2d_GBps": float(cc[0]), "d2h_GBps": float(cc[1]), "both_directions_GBps_each": float(cc[2])}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -338,16 +492,27 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": world * 1000.0 / ms_per_step, "unit": "frame-pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "one 4K frame pair per step per GPU: 12 softmax splats of fLDRnet --papermodel --test5scales "
-                                   "(2x image C=3+metric 2304x4096, 2x feature C=48 at 5 levels) + 5-level PWC correlation "
-                                   "pyramid at native 4K (B=2, C=196..32)",
-                       "flow_regime": "F1 smooth", "algorithmic_MB_per_step": round(step_bytes / 1e6, 1),
-                       "l2_policy": "inputs+outputs per step (>1.8 GB) exceed the 126 MB L2; no explicit flush",
-                       "launch_mode": launch_mode,
-                       "e2e_mode": "H2D / compute / D2H on three streams, two buffer sets, every step copies all inputs and outputs",
-                       "sharding": "frame pairs across ranks, no collective"},
+            "config": shared_config(),
+            "notes": {"l2_policy": "inputs+outputs per step (>1.8 GB) exceed the 126 MB L2; no explicit flush",
+                      "launch_mode": launch_mode,
+                      "value_eager": {"value": world * 1000.0 * args.steps / ms_eager_total, "unit": "frame-pairs/s",
+                                      "ms_per_step": ms_eager_total / args.steps,
+                                      "what": "the same K steps with eager launches on one stream (no graph)"},
+                      "e2e_mode": "H2D / compute / D2H on three streams, two buffer sets, every step copies all inputs and outputs; "
+                                  "each rank is bound to its own slice of the cores nearest its GPU before it allocates pinned memory",
+                      "host_cores_of_rank0": cores},
             "e2e": {"value": world * e2e_steps / e2e_s, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps},
+                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                    "per_rank_GBps": {"h2d": h2d_bytes * e2e_steps / e2e_s / 1e9, "d2h": d2h_bytes * e2e_steps / e2e_s / 1e9},
+                    "copy_ceiling_min_over_ranks": {k: round(v, 2) for k, v in copy_min.items()}},
+            "e2e_frames": {"value": world * e2e_steps / e2e_frames_s, "unit": "frame-pairs/s", "h2d_bytes_per_step": frames_bytes,
+                           "d2h_bytes_per_step": frames_bytes, "steps": e2e_steps,
+                           "what": "same step, but only the two frames cross PCIe (up) and the two splatted frames (down); flows, "
+                                   "metrics, features and cost volumes stay on the device as in fLDRnet's forward"},
+            "strong_scaling": {"pairs": n_pairs, "seconds": strong_ms / 1e3, "value": n_pairs / (strong_ms / 1e3), "unit": "frame-pairs/s",
+                               "pairs_per_rank": sharding.shard_counts(n_pairs, world),
+                               "what": "BASELINE configs[3]: 64 distinct pairs, pair i -> rank i mod N (sharding.run_sharded), device-timed "
+                                       "per pair (eager launches), rank time = sum over its pairs, job time = max over ranks"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": ncu_traffic(dom), "peak_source": peak_src,
@@ -356,7 +521,11 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clk,
         }
         if world == 1:
+            line["flow_regimes"] = flow_regimes_probe(splat, devin, peak)
+            line["train_step"] = train_step_probe(peak)
             line["next_rows"] = next_rows_probe(devin, peak)
+        if world == 1 and not args.no_fldrnet:
+            line["fldrnet_e2e"] = fldrnet_e2e_probe()
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(frac=1.0)
         if world == 1 and not args.no_ref_gpu:
@@ -364,6 +533,104 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------- further legs (rank 0, N = 1)
+def flow_regimes_probe(splat, devin, peak):
+    """The 4K image splat under the three flow regimes of SURVEY.md 8d (the headline step uses F1): F1 smooth, F2 iid
+    U(-64, 64) px per pixel (no merging of reductions possible), F3 every pixel converges on the frame centre (maximum
+    contention).  Device-resident, CUDA events, median of 20; inputs exceed the L2."""
+    from oracle import synth   # input generator only
+    t = [t for n, t in devin if n == "splat_image"][0]
+    N, C, H, W = t["x"].shape
+    nbytes = splat_bytes(N, C, H, W, True)
+    out = {}
+    with torch.no_grad():
+        for reg, seed in (("F1", 57), ("F2", 59), ("F3", 60)):
+            fl = synth.flow(N, H, W, reg, seed=seed).to(t["x"].device)
+            ms, lo, hi = median_event_ms(lambda: splat(t["x"], fl, t["z"]))
+            out[reg] = {"ms_per_call": round(ms, 4), "min_ms": round(lo, 4), "max_ms": round(hi, 4),
+                        "GBps": round(nbytes / ms / 1e6, 1), "frac_of_peak": round(nbytes / ms / 1e6 / peak, 3)}
+    return out
+
+
+def train_step_probe(peak):
+    """BASELINE configs[4]: the train_it.py-shaped step (main.py:545-660, utils.py:848-864) at its literal shapes - 32 synthetic
+    512x512 crops: image splat 32x3x512^2 with metric (input / flow / metric gradients), feature splat 32x48x64^2 (input
+    gradient; the flow is detached, fLDRnet.py:384), correlation B = 64 at (32,128,128) and (64,64,64) (both gradients).
+    Forward and backward are timed separately (the backward through autograd on a retained graph), CUDA events, median of
+    10; every kernel carries its roofline entry: algorithmic bytes of SURVEY.md 8d / time / measured HBM peak."""
+    import fldr_vfi_b200.correlation as C
+    import fldr_vfi_b200.softSplat as S
+    from oracle import synth   # input generator only
+    dev = torch.device("cuda", torch.cuda.current_device())
+    sp = S.Softsplat()
+    out = {}
+
+    def entry(ms, nbytes, what):
+        return {"ms": round(ms, 4), "algorithmic_bytes": int(nbytes), "GBps": round(nbytes / ms / 1e6, 1),
+                "frac_of_peak": round(nbytes / ms / 1e6 / peak, 3), "bytes_formula": what}
+
+    def splat_case(tag, N, Cc, H, W, metric, need_flow, scale):
+        x = (synth.image(N, Cc, H, W, seed=1) if Cc == 3 else synth.features(N, Cc, H, W, seed=1)).to(dev).requires_grad_(True)
+        fl = (synth.flow(N, H, W, "F1", seed=2) * scale).to(dev).requires_grad_(need_flow)
+        z = synth.metric(N, H, W, seed=3).to(dev).requires_grad_(True) if metric else None
+        g = synth.grad((N, Cc, H, W), seed=4).to(dev)
+        with torch.no_grad():
+            fwd, _, _ = median_event_ms(lambda: sp(x, fl, z), iters=10)
+        y = sp(x, fl, z)
+        wrt = [t for t in (x, fl, z) if t is not None and t.requires_grad]
+        bwd, _, _ = median_event_ms(lambda: torch.autograd.grad(y, wrt, g, retain_graph=True), iters=10)
+        px = N * H * W
+        m = 1 if metric else 0
+        out[tag + "_fwd"] = entry(fwd, 4 * px * (2 * Cc + 2 + m), "4*NHW*(2C+2+[metric])")
+        if need_flow:
+            out[tag + "_bwd"] = entry(bwd, 4 * px * (4 * Cc + 7), "4*NHW*(4C+7): all three gradients")
+        else:
+            out[tag + "_bwd"] = entry(bwd, 4 * px * (3 * Cc + 3), "4*NHW*(3C+3): grad_input only (reads gOut, out, flow, norm)")
+
+    def corr_case(tag, B, Cc, H, W):
+        a = synth.features(B, Cc, H, W, seed=3).to(dev).requires_grad_(True)
+        b = synth.features(B, Cc, H, W, seed=5).to(dev).requires_grad_(True)
+        g = synth.grad((B, 81, H, W), seed=4).to(dev)
+        with torch.no_grad():
+            fwd, _, _ = median_event_ms(lambda: C.FunctionCorrelation(tensorFirst=a, tensorSecond=b), iters=10)
+        o = C.FunctionCorrelation(tensorFirst=a, tensorSecond=b)
+        bwd, _, _ = median_event_ms(lambda: torch.autograd.grad(o, [a, b], g, retain_graph=True), iters=10)
+        px = B * H * W
+        out[tag + "_fwd"] = entry(fwd, 4 * px * (2 * Cc + 81), "4*BHW*(2C+81)")
+        out[tag + "_fwd"]["TFLOPs"] = round(162 * Cc * px / fwd / 1e9, 2)
+        out[tag + "_bwd"] = entry(bwd, 4 * px * (4 * Cc + 81), "4*BHW*(4C+81): both gradients")
+        out[tag + "_bwd"]["TFLOPs"] = round(324 * Cc * px / bwd / 1e9, 2)
+
+    splat_case("splat_image_32x3x512x512_metric", 32, 3, 512, 512, True, True, 4.0)
+    splat_case("splat_feat_32x48x64x64", 32, 48, 64, 64, False, False, 16.0)
+    corr_case("corr_64x32x128x128", 64, 32, 128, 128)
+    corr_case("corr_64x64x64x64", 64, 64, 64, 64)
+    fwd_bwd = sum(v["ms"] for v in out.values())
+    return {"kernels": out, "ms_sum": round(fwd_bwd, 3),
+            "what": "device-resident, inputs of each call exceed or fill the L2; backward timed alone on a retained autograd graph"}
+
+
+def fldrnet_e2e_probe():
+    """BASELINE configs[2] / north_star target 2: the UNTOUCHED fLDRnet (--papermodel --test5scales, shipped checkpoint) on one
+    synthetic 4096x2160 triplet, model forward wall time (synchronised both sides), 5 repetitions after one warm-up, each
+    variant in its own process: (reference) the reference's CuPy kernels through the NVRTC shim, (ours) softSplat +
+    correlation replaced by the drop-ins, (ours_warp) + the bwarp method of SURVEY 8f-1 swapped on the imported class.
+    PSNR against the synthetic ground truth per variant."""
+    import subprocess
+    script = os.path.join(ROOT, "baseline", "e2e_fldrnet.py")
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "checkpoint_dir")):
+        return {"unavailable": "baseline/_ref not staged (python baseline/fetch_ref.py in the build container)"}
+    try:
+        r = subprocess.run([sys.executable, script, "--reps", "5", "--variants", "reference,ours,ours_warp"], capture_output=True,
+                           text=True, timeout=900)
+        last = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not last:
+            return {"unavailable": ("rc %d: " % r.returncode) + (r.stderr or r.stdout)[-300:]}
+        return json.loads(last[-1])
+    except Exception as exc:      # a reported leg must never take the bench down
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
 
 
 # ----------------------------------------------------------------------------------------------- reference on the GPU
@@ -484,6 +751,7 @@ def cpu_baseline(frac):
         dt = time.perf_counter() - t0
     return {"value": frac / dt, "unit": "frame-pairs/s", "cores": os.cpu_count(),
             "kind": "reference" if use_ref else "port",
+            "kind_detail": "reference (splat) + port (correlation)" if use_ref else "port",
             "sample": f"top {frac:.3f} of the rows of every tensor of one 4K frame pair (same 17 calls), {dt:.2f} s; "
                       "splat = reference kernel text on host cores (oracle/_ref, OpenMP) + restated torch glue, "
                       "correlation = torch restatement of the reference formulas"}
@@ -520,10 +788,12 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frame-pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "one 4K frame pair per step: 12 softmax splats + 5-level correlation pyramid (see ours)",
-                       "flow_regime": "F1 smooth"},
+            "config": shared_config(),
+            "notes": {"reference_arm": "reference (splat: the reference's kernel text on host cores) + port (correlation: torch "
+                                       "restatement of the reference formulas - its updateOutput kernel needs block barriers)"},
             "cpu_baseline": {"value": value, "unit": "frame-pairs/s", "cores": os.cpu_count(),
-                             "kind": "reference" if use_ref else "port", "sample": sample},
+                             "kind": "reference" if use_ref else "port",
+                             "kind_detail": "reference (splat) + port (correlation)" if use_ref else "port", "sample": sample},
             "e2e": {"value": value, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -537,6 +807,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--no-fldrnet", action="store_true", help="skip the untouched-fLDRnet end-to-end leg (about two minutes)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay of the step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

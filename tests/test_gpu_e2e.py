@@ -29,3 +29,17 @@ def test_fldrnet_psnr_parity_with_dropins():
     assert d["with_bwarp_row"]["psnr_abs_diff_dB"] <= 0.01, d
     # ... and with torch.cuda.empty_cache() made a no-op on top (integrate.keep_allocator_cache): results unaffected
     assert d["with_bwarp_row_and_allocator_cache_kept"]["psnr_abs_diff_dB"] <= 0.01, d
+
+
+def test_fldrnet_psnr_parity_4k():
+    """north_star (c) at its literal size: 4096x2160 X-Test-shaped triplet, --papermodel --test5scales, PSNR of the
+    interpolated frame within 0.01 dB of the run with the reference's own kernels - for the two-op drop-in and with the
+    bwarp row replaced as well."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "e2e_fldrnet.py"), "--reps", "1",
+                        "--variants", "reference,ours,ours_warp"], capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert "unavailable" not in d, d
+    assert d["frame"] == "4096x2160"
+    for tag in ("ours", "ours_warp"):
+        assert d["variants"][tag]["psnr_abs_diff_dB"] <= 0.01, d

@@ -269,13 +269,18 @@ def test_plain_load_path_4k(cuda_lib, plain_loads):
 
 
 def test_4k_converge_regime_vs_oracle(cuda_lib):
-    """Flow regime F3 (every pixel flows to the frame centre: maximum contention) at the full 4K size."""
+    """Flow regime F3 (every pixel flows to the frame centre: maximum contention, ~10^6 sources per target) at the full
+    4K size.  With that many fp32 terms per pixel the summation order alone moves the result, so the bound adds 10x the
+    oracle's own fp32-vs-fp64 discrepancy per element to the north_star tolerance."""
     S = _mods(cuda_lib)
     x = synth.image(1, 3, H4K, W4K, seed=56)
     fl = synth.flow(1, H4K, W4K, "F3", seed=60)
     z = synth.metric(1, H4K, W4K, seed=58)
     y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), z.cuda(), "softmax")
-    assert_splat_close(y, so.function_softsplat(x, fl, z, "softmax"), "4K softmax F3", mag=1.0)
+    ref32 = so.function_softsplat(x, fl, z, "softmax")
+    ref64 = so.function_softsplat(x.double(), fl.double(), z.double(), "softmax")
+    assert_splat_close(y, ref64, "4K softmax F3", mag=1.0, cond=(ref32.double() - ref64).abs() + 1e-5)
+    assert float((y.cpu() == -1).float().mean()) > 0.99          # almost every pixel is a hole
 
 
 def test_unaligned_views_take_plain_load_path(cuda_lib):
