@@ -38,37 +38,6 @@ namespace cg = cooperative_groups;
 
 namespace fldr {
 
-// Target coordinate, NW corner and the four bilinear weights exactly as softSplat.py:23-38 forms them
-// (integer corner converted back to float, then subtracted).  Returns false when no corner can be in frame
-// or the coordinate is not finite (the reference device-asserts there; we skip the pixel).
-struct Corners {
-    float X, Y;
-    int x0, y0;
-    float w[4];       // NW, NE, SW, SE
-    bool valid[4];
-};
-
-__device__ __forceinline__ bool make_corners(int x, int y, float u, float v, int W, int H, Corners& k) {
-    k.X = (float)x + u;
-    k.Y = (float)y + v;
-    if (!(isfinite(k.X) && isfinite(k.Y))) return false;
-    const float fx0 = floorf(k.X), fy0 = floorf(k.Y);
-    if (fx0 < -1.f || fx0 >= (float)W || fy0 < -1.f || fy0 >= (float)H) return false;
-    k.x0 = (int)fx0;
-    k.y0 = (int)fy0;
-    const float x1f = (float)(k.x0 + 1), y1f = (float)(k.y0 + 1);
-    k.w[0] = (x1f - k.X) * (y1f - k.Y);
-    k.w[1] = (k.X - fx0) * (y1f - k.Y);
-    k.w[2] = (x1f - k.X) * (k.Y - fy0);
-    k.w[3] = (k.X - fx0) * (k.Y - fy0);
-    const bool xl = k.x0 >= 0, xr = k.x0 + 1 < W, yt = k.y0 >= 0, yb = k.y0 + 1 < H;
-    k.valid[0] = xl && yt;
-    k.valid[1] = xr && yt;
-    k.valid[2] = xl && yb;
-    k.valid[3] = xr && yb;
-    return true;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Pass 1: scatter with merged reductions.
 //
@@ -539,102 +508,116 @@ __global__ void __launch_bounds__(256) splat_fused_small_kernel(View4 in, View4 
 //   gF   = sum_c A_c * sum_corners gS_c * dw   (kernel_Softsplat_updateGradFlow, 130-155)
 //   softmax: g_x = gA_c * e^z / 2 ; g_z = e^z (sum_c gA_c x~_c + gA_C)      linear: g_x = gA_c z ; g_z = sum_c gA_c x_c + gA_C
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) splat_bwd_kernel(View4 in, View4 flow, View4 metric, const float* __restrict__ Yf,
+// One thread per source pixel of a row (grid = column blocks x rows x samples: no index division).  The 2 x 4 x C gathers of
+// grad_out and of the forward output are issued unpredicated - corners outside the frame are clamped to a loadable address
+// and deselected afterwards - so they are all in flight at once instead of one dependent DRAM latency per corner; CT = 3
+// (the image splats) unrolls the channel loop completely, CT = 0 walks the channels four at a time.
+template <int CT>
+__global__ void __launch_bounds__(128, CT ? 5 : 8) splat_bwd_kernel(View4 in, View4 flow, View4 metric, const float* __restrict__ Yf,
                                                         const float* __restrict__ norm, View4 gout,
                                                         float* __restrict__ gin, float* __restrict__ gflow,
                                                         float* __restrict__ gmetric, SplatGeom g) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= g.W) return;
+    const int y = blockIdx.y, n = blockIdx.z;
+    const int C = CT ? CT : g.C;
     const long long HW = (long long)g.H * g.W;
-    const long long total = HW * g.N;
+    const long long pix = (long long)y * g.W + x;
     const bool pre = g.mode == FLDR_SPLAT_SOFTMAX;
     const bool has_norm = g.CA > g.C;
     const float gscale = (g.mode == FLDR_SPLAT_RAW) ? 1.f : 2.f;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % g.W);
-        const int y = (int)((idx / g.W) % g.H);
-        const int n = (int)(idx / HW);
-        const long long pix = (long long)y * g.W + x;
-        const float* fp = flow.p + n * flow.sn + y * flow.sh + x * flow.sw;
-        Corners k;
-        const bool live = make_corners(x, y, __ldg(fp), __ldg(fp + flow.sc), g.W, g.H, k);
-        float* ginp = gin ? gin + (long long)n * g.C * HW + pix : nullptr;
-        if (!live) {
-            if (ginp) for (int c = 0; c < g.C; ++c) ginp[(long long)c * HW] = 0.f;
-            if (gflow) { gflow[(long long)n * 2 * HW + pix] = 0.f; gflow[(long long)n * 2 * HW + HW + pix] = 0.f; }
-            if (gmetric) gmetric[(long long)n * HW + pix] = 0.f;
-            continue;
-        }
-        float m = 1.f, z = 0.f;
-        if (g.has_metric) {
-            z = __ldg(metric.p + n * metric.sn + y * metric.sh + x * metric.sw);
-            m = (g.mode == FLDR_SPLAT_SOFTMAX) ? expf(z) : (g.mode == FLDR_SPLAT_LINEAR ? z : 1.f);
-        }
-        long long cpix[4];      // corner pixel index inside one plane
-        cpix[0] = (long long)k.y0 * g.W + k.x0;
-        cpix[1] = cpix[0] + 1;
-        cpix[2] = cpix[0] + g.W;
-        cpix[3] = cpix[2] + 1;
-        float rd[4], gsC[4];
-        bool hole[4];
+    const float* fp = flow.p + n * flow.sn + y * flow.sh + x * flow.sw;
+    const float u = __ldg(fp), v = __ldg(fp + flow.sc);
+    float z = 0.f;
+    if (g.has_metric) z = __ldg(metric.p + n * metric.sn + y * metric.sh + x * metric.sw);
+    // softSplat.py:68-83 / 114-125 (the same corner arithmetic as the forward)
+    const float X = (float)x + u, Y = (float)y + v;
+    const float fx0 = floorf(X), fy0 = floorf(Y);
+    const bool live = fx0 >= -1.f && fx0 < (float)g.W && fy0 >= -1.f && fy0 < (float)g.H;     // false for NaN / inf
+    float* ginp = gin ? gin + (long long)n * g.C * HW + pix : nullptr;
+    if (!live) {
+        if (ginp) for (int c = 0; c < C; ++c) ginp[(long long)c * HW] = 0.f;
+        if (gflow) { gflow[(long long)n * 2 * HW + pix] = 0.f; gflow[(long long)n * 2 * HW + HW + pix] = 0.f; }
+        if (gmetric) gmetric[(long long)n * HW + pix] = 0.f;
+        return;
+    }
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    const float x1f = (float)(x0 + 1), y1f = (float)(y0 + 1);
+    const float wx1 = x1f - X, wx0 = X - fx0, wy1 = y1f - Y, wy0 = Y - fy0;
+    const float w[4] = {wx1 * wy1, wx0 * wy1, wx1 * wy0, wx0 * wy0};                          // NW, NE, SW, SE
+    const bool xl = x0 >= 0, xr = x0 + 1 < g.W, yt = y0 >= 0, yb = y0 + 1 < g.H;
+    const bool valid[4] = {xl && yt, xr && yt, xl && yb, xr && yb};
+    const int xc[2] = {max(x0, 0), min(x0 + 1, g.W - 1)}, yc[2] = {max(y0, 0), min(y0 + 1, g.H - 1)};
+    int cp[4];                       // corner pixel inside a contiguous plane (clamped)
+    long long go_off[4];             // same corner in grad_out's view
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-            rd[c4] = gscale; gsC[c4] = 0.f; hole[c4] = false;
-            if (has_norm && k.valid[c4]) {
-                const float nr = __ldg(norm + (long long)n * HW + cpix[c4]);
-                hole[c4] = (nr == 0.f);
-                rd[c4] = gscale / (hole[c4] ? 1.f : nr);
-            }
-        }
-        const float wy1 = (float)(k.y0 + 1) - k.Y, wy0 = k.Y - (float)k.y0;
-        const float wx1 = (float)(k.x0 + 1) - k.X, wx0 = k.X - (float)k.x0;
-        float gfx = 0.f, gfy = 0.f, sum_gx = 0.f;
-        const float* ip = in.p + n * in.sn + y * in.sh + x * in.sw;
-        const float* gop = gout.p + n * gout.sn;
-        const float* yp = Yf ? Yf + (long long)n * g.C * HW : nullptr;
-        for (int c = 0; c < g.C; ++c) {
-            const float xv = __ldg(ip + c * in.sc);
-            const float xt = pre ? (xv + 1.f) * 0.5f : xv;
-            const float A = xt * m;
-            float gs[4];
+    for (int k = 0; k < 4; ++k) {
+        cp[k] = yc[k >> 1] * g.W + xc[k & 1];
+        go_off[k] = (long long)yc[k >> 1] * gout.sh + (long long)xc[k & 1] * gout.sw;
+    }
+    float m = 1.f;
+    if (g.has_metric) m = (g.mode == FLDR_SPLAT_SOFTMAX) ? exp_splat(z) : (g.mode == FLDR_SPLAT_LINEAR ? z : 1.f);
+    float rd[4], gsC[4] = {0.f, 0.f, 0.f, 0.f};
+    bool useq[4];
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                gs[c4] = 0.f;
-                if (k.valid[c4]) {
-                    const int cy = k.y0 + (c4 >> 1), cx = k.x0 + (c4 & 1);
-                    const float go = __ldg(gop + c * gout.sc + cy * gout.sh + cx * gout.sw);
-                    gs[c4] = go * rd[c4];
-                    if (has_norm && !hole[c4]) {
-                        const float q = __ldg(yp + (long long)c * HW + cpix[c4]) * 0.5f + 0.5f;   // S_c / norm'
-                        gsC[c4] -= gs[c4] * q;
-                    }
-                }
-            }
-            const float gA = gs[0] * k.w[0] + gs[1] * k.w[1] + gs[2] * k.w[2] + gs[3] * k.w[3];
-            if (ginp) {
-                float gx = gA;
-                if (g.mode == FLDR_SPLAT_SOFTMAX) gx = gA * m * 0.5f;
-                else if (g.mode == FLDR_SPLAT_LINEAR) gx = gA * m;
-                ginp[(long long)c * HW] = gx;
-            }
-            sum_gx += gA * xt;
-            gfx += A * ((gs[1] - gs[0]) * wy1 + (gs[3] - gs[2]) * wy0);
-            gfy += A * ((gs[2] - gs[0]) * wx1 + (gs[3] - gs[1]) * wx0);
+    for (int k = 0; k < 4; ++k) {
+        float nr = 1.f;
+        if (has_norm) nr = __ldg(norm + (long long)n * HW + cp[k]);
+        const bool hole = has_norm && nr == 0.f;
+        rd[k] = valid[k] ? __fdividef(gscale, hole ? 1.f : nr) : 0.f;
+        useq[k] = has_norm && valid[k] && !hole;
+    }
+    float gfx = 0.f, gfy = 0.f, sum_gx = 0.f;
+    const float* ip = in.p + n * in.sn + y * in.sh + x * in.sw;
+    const float* gop = gout.p + n * gout.sn;
+    const float* yp = Yf ? Yf + (long long)n * g.C * HW : nullptr;
+    auto channel = [&](int c) {
+        const float xv = __ldg(ip + c * in.sc);
+        float go[4], yq[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) go[k] = __ldg(gop + c * gout.sc + go_off[k]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) yq[k] = has_norm ? __ldg(yp + (long long)c * HW + cp[k]) : 0.f;
+        const float xt = pre ? (xv + 1.f) * 0.5f : xv;
+        const float A = xt * m;
+        float gs[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            gs[k] = valid[k] ? go[k] * rd[k] : 0.f;
+            if (useq[k]) gsC[k] -= gs[k] * (yq[k] * 0.5f + 0.5f);                             // S_c / norm'
         }
-        float gAC = 0.f;
-        if (has_norm) {
-            gAC = gsC[0] * k.w[0] + gsC[1] * k.w[1] + gsC[2] * k.w[2] + gsC[3] * k.w[3];
-            gfx += m * ((gsC[1] - gsC[0]) * wy1 + (gsC[3] - gsC[2]) * wy0);
-            gfy += m * ((gsC[2] - gsC[0]) * wx1 + (gsC[3] - gsC[1]) * wx0);
+        const float gA = gs[0] * w[0] + gs[1] * w[1] + gs[2] * w[2] + gs[3] * w[3];
+        if (ginp) {
+            float gx = gA;
+            if (g.mode == FLDR_SPLAT_SOFTMAX) gx = gA * m * 0.5f;
+            else if (g.mode == FLDR_SPLAT_LINEAR) gx = gA * m;
+            ginp[(long long)c * HW] = gx;
         }
-        if (gflow) {
-            gflow[(long long)n * 2 * HW + pix] = gfx;
-            gflow[(long long)n * 2 * HW + HW + pix] = gfy;
-        }
-        if (gmetric) {
-            float gz = sum_gx + gAC;
-            if (g.mode == FLDR_SPLAT_SOFTMAX) gz *= m;
-            gmetric[(long long)n * HW + pix] = gz;
-        }
+        sum_gx += gA * xt;
+        gfx += A * ((gs[1] - gs[0]) * wy1 + (gs[3] - gs[2]) * wy0);
+        gfy += A * ((gs[2] - gs[0]) * wx1 + (gs[3] - gs[1]) * wx0);
+    };
+    if (CT) {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) channel(c);
+    } else {
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) channel(c);
+    }
+    float gAC = 0.f;
+    if (has_norm) {
+        gAC = gsC[0] * w[0] + gsC[1] * w[1] + gsC[2] * w[2] + gsC[3] * w[3];
+        gfx += m * ((gsC[1] - gsC[0]) * wy1 + (gsC[3] - gsC[2]) * wy0);
+        gfy += m * ((gsC[2] - gsC[0]) * wx1 + (gsC[3] - gsC[1]) * wx0);
+    }
+    if (gflow) {
+        gflow[(long long)n * 2 * HW + pix] = gfx;
+        gflow[(long long)n * 2 * HW + HW + pix] = gfy;
+    }
+    if (gmetric) {
+        float gz = sum_gx + gAC;
+        if (g.mode == FLDR_SPLAT_SOFTMAX) gz *= m;
+        gmetric[(long long)n * HW + pix] = gz;
     }
 }
 
@@ -649,13 +632,6 @@ static int make_geom(int mode, int N, int C, int H, int W, bool has_metric, Spla
     g.CP = (g.CA + 3) / 4 * 4;
     g.has_metric = (has_metric && (mode == FLDR_SPLAT_LINEAR || mode == FLDR_SPLAT_SOFTMAX)) ? 1 : 0;
     return FLDR_OK;
-}
-
-static unsigned grid_for(long long total, int block) {
-    long long b = (total + block - 1) / block;
-    const long long cap = (long long)sm_count() * 64;
-    if (b > cap) b = cap;
-    return (unsigned)(b < 1 ? 1 : b);
 }
 
 struct FwdPlan {
@@ -848,10 +824,11 @@ extern "C" int fldr_splat_bwd(int mode, const float* in, const int64_t* in_strid
     if (grad_metric && !g.has_metric) return FLDR_ERR_INVALID_ARGUMENT;
     if (!grad_in && !grad_flow && !grad_metric) return FLDR_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const long long total = (long long)N * H * W;
-    splat_bwd_kernel<<<grid_for(total, 256), 256, 0, s>>>(make_view(in, in_strides), make_view(flow, flow_strides),
-                                                          make_view(metric, metric_strides), out, norm,
-                                                          make_view(grad_out, grad_out_strides), grad_in, grad_flow,
-                                                          grad_metric, g);
+    if (H > 65535 || N > 65535) return FLDR_ERR_UNSUPPORTED;
+    const dim3 grid((W + 127) / 128, H, N);
+    const View4 vin = make_view(in, in_strides), vfl = make_view(flow, flow_strides), vme = make_view(metric, metric_strides),
+                vgo = make_view(grad_out, grad_out_strides);
+    if (C == 3) splat_bwd_kernel<3><<<grid, 128, 0, s>>>(vin, vfl, vme, out, norm, vgo, grad_in, grad_flow, grad_metric, g);
+    else splat_bwd_kernel<0><<<grid, 128, 0, s>>>(vin, vfl, vme, out, norm, vgo, grad_in, grad_flow, grad_metric, g);
     return check_launch();
 }
