@@ -62,20 +62,25 @@ def worker(impl, out_path, reps, height, width):
     import torch.nn.functional as F
     from torch.autograd import Variable
     which = os.path.abspath(softSplat.__file__)
-    if impl in ("ours_warp", "ours_warp_keepcache"):
+    if impl in ("ours_warp", "ours_warp_keepcache", "ours_rows"):
         # next row: replace the bwarp METHOD on the imported class - fLDRnet.py itself stays untouched
         import fLDRnet
         sys.path.insert(0, ROOT)
         from fldr_vfi_b200.integrate import patch_bwarp
         patch_bwarp(fLDRnet)
         which += " + fldr_vfi_b200.warp.bwarp"
+        if impl == "ours_rows":
+            # ... and rank 4: the to_pca_diff name fLDRnet.py imported (block-PCA features, the first device step)
+            from fldr_vfi_b200.integrate import patch_pca
+            patch_pca(fLDRnet)
+            which += " + fldr_vfi_b200.pca.to_pca_diff"
     model_net, device, args = R.prepare_model()
     model_net.eval()
     if impl == "ours_warp_keepcache":
         from fldr_vfi_b200.integrate import keep_allocator_cache
         keep_allocator_cache()                 # torch.cuda.empty_cache() -> no-op (the reference calls it ~12x per forward)
         which += " + allocator cache kept"
-    if impl in ("ours_warp", "ours_warp_keepcache"):
+    if impl in ("ours_warp", "ours_warp_keepcache", "ours_rows"):
         from fldr_vfi_b200.integrate import patch_pwc_backward
         n_pwc = patch_pwc_backward(model_net)
         which += f" + pwc_backward on {n_pwc} decoder modules"
@@ -147,7 +152,7 @@ def compact(a):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--impl", default=None, choices=["ours", "ours_warp", "ours_warp_keepcache", "reference"])
+    ap.add_argument("--impl", default=None, choices=["ours", "ours_warp", "ours_warp_keepcache", "ours_rows", "reference"])
     ap.add_argument("--out", default=None)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--height", type=int, default=2160)

@@ -616,14 +616,15 @@ def fldrnet_e2e_probe():
     """BASELINE configs[2] / north_star target 2: the UNTOUCHED fLDRnet (--papermodel --test5scales, shipped checkpoint) on one
     synthetic 4096x2160 triplet, model forward wall time (synchronised both sides), 5 repetitions after one warm-up, each
     variant in its own process: (reference) the reference's CuPy kernels through the NVRTC shim, (ours) softSplat +
-    correlation replaced by the drop-ins, (ours_warp) + the bwarp method of SURVEY 8f-1 swapped on the imported class.
+    correlation replaced by the drop-ins, (ours_warp) + the bwarp method of SURVEY 8f-1 swapped on the imported class,
+    (ours_rows) + the to_pca_diff name of SURVEY 8f-4 swapped in the imported module.
     PSNR against the synthetic ground truth per variant."""
     import subprocess
     script = os.path.join(ROOT, "baseline", "e2e_fldrnet.py")
     if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "checkpoint_dir")):
         return {"unavailable": "baseline/_ref not staged (python baseline/fetch_ref.py in the build container)"}
     try:
-        r = subprocess.run([sys.executable, script, "--reps", "5", "--variants", "reference,ours,ours_warp"], capture_output=True,
+        r = subprocess.run([sys.executable, script, "--reps", "5", "--variants", "reference,ours,ours_warp,ours_rows"], capture_output=True,
                            text=True, timeout=900)
         last = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
         if r.returncode != 0 or not last:
@@ -674,6 +675,18 @@ def next_rows_probe(devin, peak):
     nbytes = px * (6 * 4 + 6 * C * 4 + C * 8)
     out["occ_blend_C3_f64"] = {"ms_per_call": round(ms, 4), "algorithmic_bytes": nbytes, "GBps": round(nbytes / ms / 1e6, 1),
                                "frac_of_peak": round(nbytes / ms / 1e6 / peak, 3)}
+    # rank 4: block-PCA features of the two stacked frames (pca_comp.py:473-528), float32 result (the .float() of fLDRnet.py:146)
+    import fldr_vfi_b200.pca as Pc
+    g = torch.Generator().manual_seed(5)
+    mean = (torch.randn(64, generator=g, dtype=torch.float64) * 0.1).to(x0.device)
+    EV = torch.linalg.qr(torch.randn(64, 64, generator=g, dtype=torch.float64))[0][:16].contiguous().to(x0.device)
+    mv = (torch.rand(16, generator=g, dtype=torch.float64) + 0.5).to(x0.device)
+    im6 = torch.cat([x0[0], x1[0]], 0)
+    with torch.no_grad():
+        ms = med(lambda: Pc.pca_features(im6, mean, EV, mv, out_dtype=torch.float32))
+    nbytes = 6 * H * W * 4 + 6 * 16 * (H // 8) * (W // 8) * 4
+    out["pca_features_6xHxW_f32out"] = {"ms_per_call": round(ms, 4), "algorithmic_bytes": nbytes, "GBps": round(nbytes / ms / 1e6, 1),
+                                        "frac_of_peak": round(nbytes / ms / 1e6 / peak, 3)}
     return out
 
 

@@ -50,6 +50,10 @@ SYMBOLS = {
     "fldr_occ_blend_fwd": (ctypes.c_int, [c_float_p, c_i64_p, ctypes.POINTER(ctypes.c_void_p), c_i64_p, c_float_p,
                                           ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "fldr_pca_features_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 5),
+    "fldr_pca_features_fwd": (ctypes.c_int, [c_float_p, c_i64_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
 }
 
 SPLAT_MODES = {"summation": 0, "average": 1, "linear": 2, "softmax": 3, "raw": 4}

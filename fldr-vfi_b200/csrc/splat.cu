@@ -825,10 +825,11 @@ extern "C" int fldr_splat_bwd(int mode, const float* in, const int64_t* in_strid
     if (!grad_in && !grad_flow && !grad_metric) return FLDR_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (H > 65535 || N > 65535) return FLDR_ERR_UNSUPPORTED;
-    const dim3 grid((W + 127) / 128, H, N);
+    const int bx = W >= 128 ? 128 : ((W + 31) / 32) * 32;          // narrow frames: no idle lanes beyond the row
+    const dim3 grid((W + bx - 1) / bx, H, N);
     const View4 vin = make_view(in, in_strides), vfl = make_view(flow, flow_strides), vme = make_view(metric, metric_strides),
                 vgo = make_view(grad_out, grad_out_strides);
-    if (C == 3) splat_bwd_kernel<3><<<grid, 128, 0, s>>>(vin, vfl, vme, out, norm, vgo, grad_in, grad_flow, grad_metric, g);
-    else splat_bwd_kernel<0><<<grid, 128, 0, s>>>(vin, vfl, vme, out, norm, vgo, grad_in, grad_flow, grad_metric, g);
+    if (C == 3) splat_bwd_kernel<3><<<grid, bx, 0, s>>>(vin, vfl, vme, out, norm, vgo, grad_in, grad_flow, grad_metric, g);
+    else splat_bwd_kernel<0><<<grid, bx, 0, s>>>(vin, vfl, vme, out, norm, vgo, grad_in, grad_flow, grad_metric, g);
     return check_launch();
 }

@@ -30,6 +30,30 @@ def patch_bwarp(fldrnet_module):
     return original
 
 
+def patch_pca(fldrnet_module):
+    """Replace the ``to_pca_diff`` name ``fLDRnet.py`` imported from ``pca_comp`` (fLDRnet.py:18, called at 146) by the fused
+    block-PCA kernels.  Calls the replacement does not cover (CPU tensors, parameters that require grad,
+    block sizes other than 8) go to the reference's own function.  Returns the original function (assign it back to undo)."""
+    from .pca import pca_features
+    original = fldrnet_module.to_pca_diff
+    if getattr(original, "_fldr_b200_patched", False):
+        return original._fldr_b200_original
+
+    def to_pca_diff(im, params, args, mean, EV, mean_vec):
+        im_t = torch.as_tensor(im)
+        ok = (im_t.is_cuda and im_t.dtype == torch.float32 and params.wiS == 8 and mean.dtype == torch.float64 and EV.dtype == torch.float64
+              and EV.shape[0] <= 16 and EV.shape[0] == int(64 * params.components_fraction)
+              and not (torch.is_grad_enabled() and (mean.requires_grad or EV.requires_grad or im_t.requires_grad)))
+        if not ok:
+            return original(im, params, args, mean, EV, mean_vec)
+        return pca_features(im_t, mean, EV, mean_vec if args.mean_vector_norm else None)
+
+    to_pca_diff._fldr_b200_patched = True
+    to_pca_diff._fldr_b200_original = original
+    fldrnet_module.to_pca_diff = to_pca_diff
+    return original
+
+
 def patch_pwc_backward(model):
     """Route every ``Backward(tensorInput, tensorFlow, grid_cache, ones_cache)`` method found on the sub-modules of a
     built model (PWC-Net's decoders, OpticalFlow/PWCNet.py:116-143 - the classes are local to ``Network.__init__``, so

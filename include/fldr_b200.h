@@ -16,6 +16,7 @@
  *   fldr_bwarp_fwd, fldr_warp_metric_fwd  <- fLDRnet.py:546-581 DCTVFInet.bwarp and the metric at 442-446
  *                       (the step just before the image splat)
  *   fldr_occ_blend_fwd  <- fLDRnet.py:510-524 occlusion softmax + six-way blend (the last step; 8f rank 2)
+ *   fldr_pca_features_fwd  <- pca_comp.py:473-528 to_pca_diff, called at fLDRnet.py:146 (the first device step; 8f rank 4)
  *
  * Conventions
  *   - plain C: raw device pointers, explicit element strides, explicit sizes, a CUDA stream handle.
@@ -208,6 +209,27 @@ int fldr_occ_blend_fwd(const float* logits, const int64_t* logits_strides,
                        const float* const* images, const int64_t* image_strides,
                        const float* t_value, int64_t t_stride, const double* temperature,
                        double* out, double* occ0, int N, int C, int H, int W, fldr_stream_t stream);
+
+/* ------------------------------------- block-PCA feature extraction (next row) -------------------------- */
+
+/* Scratch of fldr_pca_features_fwd: the min / max words (+ the float64 intermediate when the output is float32). */
+size_t fldr_pca_features_workspace_bytes(int chan, int H, int W, int ncomp, int out_is_f32);
+
+/*
+ * pca_comp.py:473-528 `to_pca_diff(im, params, args, mean, EV, mean_vec)` with params.wiS = 8, the first device step of every
+ * fLDRnet forward (fLDRnet.py:146), in float64 like the reference:
+ *   t[c*ncomp + k, yb, xb] = sum_j (im[c, 8 yb + j / 8, 8 xb + j % 8] - mean[j]) * EV[k][j]     ( / mean_vec[k] if given )
+ *   out = ((t - min t) / (max t - min t)) * 2 - 1              (min / max over the whole tensor, pca_comp.py:521-526)
+ *   im        [chan, H, W] float32, strides im_strides[3] in elements (unit pixel stride); H, W multiples of 8
+ *             (anything else returns FLDR_ERR_INVALID_ARGUMENT where the reference raises, 486-487)
+ *   mean      [64] float64;  ev [ncomp <= 16][64] float64, ev_row_stride elements between rows (EV.permute(1,0) of 507 is
+ *             folded into the indexing);  mean_vec [ncomp] float64 or NULL (args.mean_vector_norm off)
+ *   out       [chan * ncomp, H/8, W/8] contiguous, float64 (out_is_f32 = 0: what the reference returns) or float32
+ *             (out_is_f32 = 1: the `.float()` the caller applies at fLDRnet.py:146, fused)
+ */
+int fldr_pca_features_fwd(const float* im, const int64_t* im_strides, const double* mean, const double* ev,
+                          int64_t ev_row_stride, const double* mean_vec, void* out, int out_is_f32,
+                          int chan, int H, int W, int ncomp, void* ws, size_t ws_bytes, fldr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ oracle/splat_oracle.py (softSplat.py:320-352) around the reference kernels.
 """
 import os
 import sys
+import textwrap
 
 import numpy as np
 import torch
@@ -155,7 +156,39 @@ def blend_case(name, N, C, H, W, seed, temperature=1.0, t=0.5):
     print(name, tuple(ns["out_l"].shape), ns["out_l"].dtype)
 
 
+def pca_case(name, chan, H, W, seed, mean_vector_norm):
+    """pca_comp.py's own ``to_pca_diff`` (473-528), lifted by ast and executed on the CPU in float64 as the model does
+    (fLDRnet.py:146: float32 frames, float64 mean / eigenvectors / mean_vec parameters)."""
+    import ast
+    import types
+    import torch.nn as nn
+    src = open("/root/reference/pca_comp.py").read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "to_pca_diff")
+    code = textwrap.dedent("\n".join(src.splitlines()[fn.lineno - 1:fn.end_lineno]))
+    import time
+    ns = {"torch": torch, "nn": nn, "time": time}
+    exec(compile(code, "pca_comp.py:to_pca_diff", "exec"), ns)
+    g = torch.Generator().manual_seed(seed)
+    im = synth.image(1, chan, H, W, seed=seed)[0]                                 # [chan, H, W] float32 in [-1, 1]
+    mean = torch.randn(64, generator=g, dtype=torch.float64) * 0.1
+    EV = torch.linalg.qr(torch.randn(64, 64, generator=g, dtype=torch.float64))[0][:16].contiguous()   # orthonormal rows
+    mean_vec = torch.rand(16, generator=g, dtype=torch.float64) + 0.5
+    params = types.SimpleNamespace(wiS=8, weightMat=None, components_fraction=0.25)
+    args = types.SimpleNamespace(gpu="cpu", mean_vector_norm=mean_vector_norm)
+    with torch.no_grad():
+        out = ns["to_pca_diff"](im, params, args, mean, EV, mean_vec)
+    assert out.dtype == torch.float64 and tuple(out.shape) == (chan * 16, H // 8, W // 8)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), im=im.numpy(), mean=mean.numpy(), EV=EV.numpy(), mean_vec=mean_vec.numpy(),
+                        mean_vector_norm=np.int32(mean_vector_norm), out=out.numpy())
+    print(name, tuple(out.shape), out.dtype, float(out.min()), float(out.max()))
+
+
 if __name__ == "__main__":
+    if "--pca-only" in sys.argv:
+        pca_case("pca_6x32x48", 6, 32, 48, 410, True)          # one sample (two RGB frames), mean-vector normalisation on
+        pca_case("pca_12x16x24_nomv", 12, 16, 24, 420, False)  # B = 2, no mean-vector normalisation
+        pca_case("pca_6x8x8", 6, 8, 8, 430, True)              # a single block per channel
+        sys.exit(0)
     if "--blend-only" in sys.argv:
         blend_case("blend_t05", 2, 3, 16, 24, 210)                       # t = 0.5 / 0.55, T = 1 (the shipped checkpoint)
         blend_case("blend_temp", 1, 3, 9, 13, 220, temperature=0.37, t=0.25)   # odd sizes, learned temperature, t != 0.5

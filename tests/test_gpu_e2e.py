@@ -36,10 +36,11 @@ def test_fldrnet_psnr_parity_4k():
     interpolated frame within 0.01 dB of the run with the reference's own kernels - for the two-op drop-in and with the
     bwarp row replaced as well."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "e2e_fldrnet.py"), "--reps", "1",
-                        "--variants", "reference,ours,ours_warp"], capture_output=True, text=True, timeout=1200)
+                        "--variants", "reference,ours,ours_warp,ours_rows"], capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert "unavailable" not in d, d
     assert d["frame"] == "4096x2160"
-    for tag in ("ours", "ours_warp"):
+    for tag in ("ours", "ours_warp", "ours_rows"):
         assert d["variants"][tag]["psnr_abs_diff_dB"] <= 0.01, d
+    assert "pca.to_pca_diff" in d["variants"]["ours_rows"]["ops"]

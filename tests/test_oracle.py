@@ -242,3 +242,22 @@ def test_blend_kat():
     logits[:, 3] = 800.0
     out, _ = bo.occ_blend(logits, T, torch.full((N, 1), 0.3), *imgs)
     assert float((out - imgs[3].double()).abs().max()) < 1e-12
+
+
+# ------------------------------------------------------------------ block-PCA features
+@pytest.mark.parametrize("name", ["pca_6x32x48", "pca_12x16x24_nomv", "pca_6x8x8"])
+def test_pca_restatement_vs_reference_text(name):
+    """oracle/pca_oracle.py against the golden vectors produced by the reference's own to_pca_diff text (float64)."""
+    from oracle import pca_oracle
+    g = load_golden(name)
+    mv = g["mean_vec"] if int(g["mean_vector_norm"]) else None
+    out = pca_oracle.to_pca_diff(g["im"], g["mean"], g["EV"], mv)
+    assert out.dtype == torch.float64 and out.shape == g["out"].shape
+    assert float((out - g["out"]).abs().max()) <= 1e-13
+    assert float(out.min()) == -1.0 and float(out.max()) == 1.0
+
+
+def test_pca_rejects_unpadded_frames():
+    from oracle import pca_oracle
+    with pytest.raises(Exception):
+        pca_oracle.to_pca_diff(torch.zeros(6, 12, 16), torch.zeros(64, dtype=torch.float64), torch.zeros(16, 64, dtype=torch.float64))
