@@ -69,6 +69,14 @@ def pwc_backward():
     return lambda tensorInput, tensorFlow: ns["Backward"](None, tensorInput, tensorFlow, grid, ones)
 
 
+def to_pca_diff():
+    """``f(im, params, args, mean, EV, mean_vec)``: the reference's own function text (pca_comp.py:473-528)."""
+    import time
+    ns = {"torch": torch, "nn": torch.nn, "time": time}
+    exec(compile(_function_source(os.path.join(REFDIR, "pca_comp.py"), "to_pca_diff"), "pca_comp.py:to_pca_diff", "exec"), ns)
+    return ns["to_pca_diff"]
+
+
 def blend():
     """``f(refine_out, T_param, t_value, warped0, warped1, im0_tot, im1_tot, x_l) -> (out_l, occ_0_l)`` executing the
     reference's statements from ``num_softmax_combs = 6`` to ``out_l /=divisor``."""

@@ -686,7 +686,20 @@ def next_rows_probe(devin, peak):
         ms = med(lambda: Pc.pca_features(im6, mean, EV, mv, out_dtype=torch.float32))
     nbytes = 6 * H * W * 4 + 6 * 16 * (H // 8) * (W // 8) * 4
     out["pca_features_6xHxW_f32out"] = {"ms_per_call": round(ms, 4), "algorithmic_bytes": nbytes, "GBps": round(nbytes / ms / 1e6, 1),
-                                        "frac_of_peak": round(nbytes / ms / 1e6 / peak, 3)}
+                                        "frac_of_peak": round(nbytes / ms / 1e6 / peak, 3),
+                                        "bound_note": "float64 FMA rate of the CUDA cores, not HBM (1.8 GFLOP of float64 per call)"}
+    try:      # the reference's own function text on the same GPU (torch operator sequence incl. a float64 matmul)
+        import types
+        from baseline import ref_src
+        if ref_src.available():
+            ref_fn = ref_src.to_pca_diff()
+            prm = types.SimpleNamespace(wiS=8, weightMat=None, components_fraction=0.25)
+            rargs = types.SimpleNamespace(gpu=x0.device, mean_vector_norm=True)
+            with torch.no_grad():
+                ms_ref = med(lambda: ref_fn(im6, prm, rargs, mean, EV, mv).float())
+            out["pca_features_6xHxW_f32out"]["reference_text_same_gpu_ms"] = round(ms_ref, 4)
+    except Exception as exc:      # a reported baseline must never take the bench down
+        out["pca_features_6xHxW_f32out"]["reference_text_same_gpu_ms"] = f"unavailable: {type(exc).__name__}"
     return out
 
 

@@ -3,8 +3,9 @@
 // reshape / permute copies), subtracts the mean block, multiplies by the eigenvector matrix in float64 (cuBLAS DGEMM
 // [blocks, 64] x [64, 16]), optionally divides by mean_vec, permutes to [chan * 16, H/8, W/8], takes a global min / max
 // (two reductions) and rescales to [-1, 1]: ~12 kernels and five float64 temporaries of the frame's size.  Here:
-//   pass 1  pca_project_kernel   reads the float32 frame once (coalesced 8-row stripes staged in shared memory), projects
-//                                every block on the eigenvectors in float64 in the order sum_j (x_j - mean_j) * EV[k][j],
+//   pass 1  pca_project_kernel   reads the float32 frame once (coalesced 8-row stripes, converted and centred into shared
+//                                memory), projects every block on the eigenvectors in float64 with a 4 x 4 register tile
+//                                per thread, in the order sum_j (x_j - mean_j) * EV[k][j],
 //                                writes the result already permuted, and folds the global min / max into two 64-bit
 //                                atomics (order-preserving bit pattern)
 //   pass 2  pca_rescale_kernel   ((t - min) / (max - min)) * 2 - 1, float64 like the reference or straight to the float32
@@ -14,8 +15,13 @@
 
 namespace fldr {
 namespace pca {
-constexpr int WS = 8, NV = WS * WS, NBLK = 16, NT = 256;      // 16 blocks (128 pixels of a stripe) x 16 components per CTA
-constexpr int EVP = NV + 1;                                   // eigenvector row pitch in shared memory: no bank conflicts
+constexpr int WS = 8, NV = WS * WS;
+constexpr int NBLK = 64;                  // blocks of a stripe per CTA (512 pixels x 8 rows)
+constexpr int BG = 4, KG = 4;             // register blocking: a thread owns 4 adjacent blocks x 4 components
+constexpr int NT = (NBLK / BG) * (16 / KG);      // 64 threads
+constexpr int EVP = NV + 1;               // eigenvector row pitch in shared memory (doubles): conflict-free across components
+constexpr int LP = NBLK * WS + 2 * (NBLK / BG) + 2;   // row pitch of the centred stripe (doubles), 2 doubles of skew per 4 blocks
+__host__ __device__ constexpr int lcol(int xx) { return xx + ((xx >> 5) << 1); }   // block groups land 4 banks apart: conflict-free
 }  // namespace pca
 
 __device__ __forceinline__ unsigned long long ordered_bits(double v) {
@@ -29,53 +35,77 @@ __host__ __device__ inline double from_ordered_bits(unsigned long long o) {
     return v;
 }
 
-// grid (ceil(bx / 16), by, chan); thread = (block of the stripe, component)
+// grid (ceil(bx / 64), by, chan).  Phase 1: the 8 x 512 float32 stripe is read once (coalesced), converted to float64 and
+// centred (x - mean, pca_comp.py:502) into shared memory.  Phase 2: a thread accumulates a 4-block x 4-component register
+// tile - 8 shared-memory loads feed 16 DFMA per pixel of the block, so the float64 pipe, not the LSU, is the limit.
 __global__ void __launch_bounds__(pca::NT) pca_project_kernel(const float* __restrict__ im, long long s_c, long long s_h,
                                                               const double* __restrict__ mean, const double* __restrict__ ev,
                                                               long long ev_stride, const double* __restrict__ mean_vec,
                                                               double* __restrict__ t, unsigned long long* __restrict__ mm,
                                                               int chan, int by, int bx, int ncomp) {
     using namespace pca;
-    __shared__ float tile[WS][NBLK * WS];
-    __shared__ double s_ev[16 * EVP];
-    __shared__ double s_mean[NV];
-    __shared__ unsigned long long s_mm[2];
+    extern __shared__ __align__(16) double smem_d[];
+    double* s_loc = smem_d;                       // [WS][LP]
+    double* s_ev = s_loc + WS * LP;               // [16][EVP]
+    double* s_mean = s_ev + 16 * EVP;             // [NV]
     const int tid = threadIdx.x;
     const int c = blockIdx.z, yb = blockIdx.y, xb0 = blockIdx.x * NBLK;
     const int W = bx * WS;
-    for (int e = tid; e < ncomp * NV; e += NT) s_ev[(e / NV) * EVP + (e % NV)] = ev[(long long)(e / NV) * ev_stride + (e % NV)];
+    for (int e = tid; e < 16 * NV; e += NT) s_ev[(e / NV) * EVP + (e % NV)] = (e / NV < ncomp) ? ev[(long long)(e / NV) * ev_stride + (e % NV)] : 0.0;
     if (tid < NV) s_mean[tid] = mean[tid];
-    if (tid < 2) s_mm[tid] = 0ull;
+    __syncthreads();
     const float* src = im + c * s_c + (long long)(yb * WS) * s_h + xb0 * WS;
     for (int e = tid; e < WS * NBLK * WS; e += NT) {
         const int r = e / (NBLK * WS), xx = e % (NBLK * WS);
-        tile[r][xx] = (xb0 * WS + xx < W) ? __ldg(src + r * s_h + xx) : 0.f;
+        const float v = (xb0 * WS + xx < W) ? __ldg(src + r * s_h + xx) : 0.f;
+        s_loc[r * LP + lcol(xx)] = (double)v - s_mean[r * WS + (xx & 7)];                           // pca_comp.py:502
     }
     __syncthreads();
-    const int blk = tid / 16, k = tid % 16;
-    const int xb = xb0 + blk;
-    double acc = 0.0;
-    bool live = xb < bx && k < ncomp;
-    if (live) {
-#pragma unroll 8
-        for (int j = 0; j < NV; ++j) {
-            const double loc = (double)tile[j >> 3][blk * WS + (j & 7)] - s_mean[j];          // pca_comp.py:502
-            acc = fma(loc, s_ev[k * EVP + j], acc);                                           // 507
-        }
-        if (mean_vec) acc = acc / mean_vec[k];                                                // 510-511
-        t[((long long)(c * ncomp + k) * by + yb) * bx + xb] = acc;                            // 516-518: [chan*ncomp, by, bx]
+    const int bg = tid / (16 / KG), kg = tid % (16 / KG);          // block group, component group
+    double acc[BG][KG];
+#pragma unroll
+    for (int b = 0; b < BG; ++b)
+#pragma unroll
+        for (int k = 0; k < KG; ++k) acc[b][k] = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < NV; ++j) {
+        double e4[KG], l4[BG];
+#pragma unroll
+        for (int k = 0; k < KG; ++k) e4[k] = s_ev[(kg * KG + k) * EVP + j];
+#pragma unroll
+        for (int b = 0; b < BG; ++b) l4[b] = s_loc[(j >> 3) * LP + lcol((bg * BG + b) * WS) + (j & 7)];
+#pragma unroll
+        for (int b = 0; b < BG; ++b)
+#pragma unroll
+            for (int k = 0; k < KG; ++k) acc[b][k] = fma(l4[b], e4[k], acc[b][k]);            // 507, j ascending
     }
-    // global min / max (521-522): warp reduce on the order-preserving bit patterns, one atomic pair per CTA
-    unsigned long long hi = live ? ordered_bits(acc) : 0ull, lo = live ? ~ordered_bits(acc) : 0ull;
+    unsigned long long hi = 0ull, lo = 0ull;
+#pragma unroll
+    for (int k = 0; k < KG; ++k) {
+        const int kk = kg * KG + k;
+        if (kk < ncomp) {
+            const double mv = mean_vec ? mean_vec[kk] : 1.0;
+#pragma unroll
+            for (int b = 0; b < BG; ++b) {
+                const int xb = xb0 + bg * BG + b;
+                if (xb < bx) {
+                    const double v = mean_vec ? acc[b][k] / mv : acc[b][k];                    // 510-511
+                    t[((long long)(c * ncomp + kk) * by + yb) * bx + xb] = v;                  // 516-518: [chan*ncomp, by, bx]
+                    const unsigned long long o = ordered_bits(v);
+                    hi = o > hi ? o : hi;
+                    lo = ~o > lo ? ~o : lo;
+                }
+            }
+        }
+    }
+    // global min / max (521-522): warp reduce on the order-preserving bit patterns, one atomic pair per warp
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long h2 = __shfl_xor_sync(0xffffffffu, hi, o), l2 = __shfl_xor_sync(0xffffffffu, lo, o);
         hi = h2 > hi ? h2 : hi;
         lo = l2 > lo ? l2 : lo;
     }
-    if ((tid & 31) == 0) { atomicMax(&s_mm[0], hi); atomicMax(&s_mm[1], lo); }
-    __syncthreads();
-    if (tid == 0) { atomicMax(&mm[0], s_mm[0]); atomicMax(&mm[1], s_mm[1]); }
+    if ((tid & 31) == 0) { atomicMax(&mm[0], hi); atomicMax(&mm[1], lo); }
 }
 
 template <typename OutT>
@@ -113,7 +143,8 @@ extern "C" int fldr_pca_features_fwd(const float* im, const int64_t* im_strides,
     if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
     const int by = H / 8, bx = W / 8;
     dim3 grid((bx + pca::NBLK - 1) / pca::NBLK, by, chan);
-    pca_project_kernel<<<grid, pca::NT, 0, s>>>(im, im_strides[0], im_strides[1], mean, ev, ev_row_stride, mean_vec, t, mm, chan,
+    const size_t smem = (size_t)(pca::WS * pca::LP + 16 * pca::EVP + pca::NV) * sizeof(double);     // ~41 KB
+    pca_project_kernel<<<grid, pca::NT, smem, s>>>(im, im_strides[0], im_strides[1], mean, ev, ev_row_stride, mean_vec, t, mm, chan,
                                                 by, bx, ncomp);
     int st = check_launch();
     if (st != FLDR_OK) return st;
