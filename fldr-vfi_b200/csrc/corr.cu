@@ -7,7 +7,7 @@
 //   corr81_fwd_tma_kernel   persistent CTAs, 3-stage mbarrier ring refilled by the last warp out of a chunk;
 //                           channel-split + red.global.add.v4 for levels with fewer tiles than SMs
 //   corr81_fwd_kernel       plain-load fallback (W % 4 != 0, unaligned or exotic views)
-//   corr81_bwd_tile_kernel  both gradients (gradSecond through the shifted planes built by corr81_bwd_shift_kernel)
+//   corr81_bwd_tile_kernel  both gradients in one launch (gradSecond gathers the shifted gradOut tile itself)
 #include <string.h>
 
 #include "common.cuh"
@@ -388,11 +388,17 @@ __device__ __forceinline__ void bwd_tile_compute(const float* __restrict__ sA, c
     }
 }
 
-// TMA: A tile and F chunk arrive as two bulk tensor loads (zero fill outside the frame / beyond C) on one mbarrier
+// One launch serves both gradients: blockIdx.z < nfirst * B works on gradFirst (A = gradOut as it is, F = second), the rest on
+// gradSecond (F = first, A = gradOut read THROUGH the shift: A[(q,r)][y][x] = gradOut[(-q,-r)][y+q][x+r], zero outside the
+// frame - correlation.py:200-236 with q = -p, r = -o).  The shifted tile is gathered by the CTA's threads straight from
+// gradOut (81 coalesced row segments per thread position) while the TMA unit fetches the F chunk, so the 81-plane shifted copy
+// the first version materialised in a workspace (one write + one read of 81*B*H*W floats, and a launch) is gone.
+// TMA: the unshifted A tile and every F chunk arrive as bulk tensor loads (zero fill outside the frame / beyond C).
 template <bool TMA>
 __global__ void __launch_bounds__(bwd::NT, 2)
-corr81_bwd_tile_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmA, View4 F, View4 A,
-                       float* __restrict__ G, int C, int H, int W, float rc) {
+corr81_bwd_tile_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_constant__ CUtensorMap tmF2,
+                       const __grid_constant__ CUtensorMap tmA, View4 F1, View4 F2, View4 A, float* __restrict__ G1,
+                       float* __restrict__ G2, int B, int nfirst, int C, int H, int W, float rc) {
     using namespace bwd;
     extern __shared__ __align__(128) float smem_f[];
     float* sA = smem_f;                       // [81][TH][TW]
@@ -400,17 +406,35 @@ corr81_bwd_tile_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_con
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_f + A_FLOATS + F_FLOATS);
     const int tid = threadIdx.x;
     const int pg = tid & 7, row = (tid >> 3) & 3, cg = tid >> 5;
-    const int x0t = blockIdx.x * TW, y0t = blockIdx.y * TH, b = blockIdx.z;
+    const int x0t = blockIdx.x * TW, y0t = blockIdx.y * TH;
+    const bool second = (int)blockIdx.z >= nfirst * B;            // which gradient this CTA works on
+    const int b = second ? blockIdx.z - nfirst * B : blockIdx.z;
+    const CUtensorMap* tmF = second ? &tmF2 : &tmF1;
+    const View4& F = second ? F2 : F1;
+    float* G = second ? G2 : G1;
     uint32_t phase = 0;
     if (TMA) {
         if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
         __syncthreads();
         if (tid == 0) {
-            mbar_arrive_expect_tx(bar, (A_FLOATS + F_FLOATS) * 4);
-            tma_load_4d(sA, &tmA, bar, x0t, y0t, 0, b);
-            tma_load_4d(sF, &tmF, bar, x0t - kPad, y0t - kPad, 0, b);
+            mbar_arrive_expect_tx(bar, ((second ? 0 : A_FLOATS) + F_FLOATS) * 4);
+            if (!second) tma_load_4d(sA, &tmA, bar, x0t, y0t, 0, b);
+            tma_load_4d(sF, tmF, bar, x0t - kPad, y0t - kPad, 0, b);
         }
-    } else {
+    }
+    if (second) {
+        // shifted gather: thread (r, xx) of the 4 x 32 tile fills its position of all 81 planes
+        const int r = tid >> 5, xx = tid & 31;
+        const float* pa = A.p + b * A.sn;
+#pragma unroll 9
+        for (int t = 0; t < 81; ++t) {
+            const int q = t / kD - kPad, rr = t % kD - kPad;
+            const int gy = y0t + r + q, gx = x0t + xx + rr;
+            float v = 0.f;
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(pa + (80 - t) * A.sc + gy * A.sh + gx * A.sw);
+            sA[t * (TH * TW) + tid] = v;
+        }
+    } else if (!TMA) {
         const float* pa = A.p + b * A.sn;
         for (int e = tid; e < A_FLOATS; e += NT) {
             const int t = e / (TH * TW), r = (e / TW) % TH, xx = e % TW;
@@ -422,12 +446,10 @@ corr81_bwd_tile_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_con
     const long long HW = (long long)H * W;
     for (int c0 = 0; c0 < C; c0 += CK) {
         if (TMA) {
-            if (c0 > 0) {
-                __syncthreads();                       // everyone is done reading the previous chunk
-                if (tid == 0) {
-                    mbar_arrive_expect_tx(bar, F_FLOATS * 4);
-                    tma_load_4d(sF, &tmF, bar, x0t - kPad, y0t - kPad, c0, b);
-                }
+            __syncthreads();                           // c0 == 0: the gathered A tile is complete; later: the previous chunk was read
+            if (c0 > 0 && tid == 0) {
+                mbar_arrive_expect_tx(bar, F_FLOATS * 4);
+                tma_load_4d(sF, tmF, bar, x0t - kPad, y0t - kPad, c0, b);
             }
             mbar_wait(bar, phase);
             phase ^= 1;
@@ -455,7 +477,7 @@ corr81_bwd_tile_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_con
                 const int c = c0 + cg * 8 + cc;
                 if (c < C) {
                     float* gp = G + ((long long)b * C + c) * HW + (long long)y * W + x;
-                    if ((W & 3) == 0) {
+                    if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0) {
                         __stcs(reinterpret_cast<float4*>(gp), make_float4(acc[cc][0] * rc, acc[cc][1] * rc, acc[cc][2] * rc, acc[cc][3] * rc));
                     } else {
 #pragma unroll
@@ -466,20 +488,6 @@ corr81_bwd_tile_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_con
             }
         }
     }
-}
-
-// G2[b][t'][y][x] = gradOut[b][80 - t'][y + q][x + r] for t' = (q+4)*9 + (r+4), zero when (y+q, x+r) leaves the frame
-__global__ void __launch_bounds__(256) corr81_bwd_shift_kernel(View4 gout, float* __restrict__ g2, int H, int W) {
-    const long long HW = (long long)H * W;
-    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (idx >= HW) return;
-    const int x = (int)(idx % W), y = (int)(idx / W);
-    const int t = blockIdx.y, b = blockIdx.z;
-    const int q = t / kD - kPad, r = t % kD - kPad;
-    const int yy = y + q, xx = x + r;
-    float v = 0.f;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(gout.p + b * gout.sn + (80 - t) * gout.sc + yy * gout.sh + xx * gout.sw);
-    g2[((long long)b * 81 + t) * HW + idx] = v;
 }
 
 static int check_corr_args(int B, int C, int H, int W) {
@@ -544,61 +552,44 @@ extern "C" int fldr_corr81_fwd_act(const float* first, const int64_t* first_stri
 }
 
 extern "C" size_t fldr_corr81_bwd_workspace_bytes(int B, int C, int H, int W) {
-    (void)C;
-    if (B <= 0 || H <= 0 || W <= 0) return 0;
-    return align_up((size_t)B * 81 * H * W * sizeof(float), 256);      // G2 for gradSecond
+    (void)B; (void)C; (void)H; (void)W;
+    return 0;          // the shifted gradOut tile is gathered inside the kernel: no scratch
 }
 
 extern "C" int fldr_corr81_bwd(const float* first, const int64_t* first_strides, const float* second,
                                const int64_t* second_strides, const float* grad_out, const int64_t* grad_out_strides,
                                float* grad_first, float* grad_second, int B, int C, int H, int W, void* ws,
                                size_t ws_bytes, fldr_stream_t stream) {
+    (void)ws; (void)ws_bytes;
     int st = check_corr_args(B, C, H, W);
     if (st != FLDR_OK) return st;
     if (!first || !second || !first_strides || !second_strides || !grad_out || !grad_out_strides)
         return FLDR_ERR_INVALID_ARGUMENT;
-    if (grad_second && (!ws || ws_bytes < fldr_corr81_bwd_workspace_bytes(B, C, H, W))) return FLDR_ERR_WORKSPACE_TOO_SMALL;
+    if (!grad_first && !grad_second) return FLDR_OK;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const float rc = 1.0f / (float)C;
     const View4 vg = make_view(grad_out, grad_out_strides);
     const View4 v1 = make_view(first, first_strides), v2 = make_view(second, second_strides);
-    dim3 grid((W + bwd::TW - 1) / bwd::TW, (H + bwd::TH - 1) / bwd::TH, B);
-    const long long HW = (long long)H * W;
-    auto launch = [&](const View4& F, const View4& A, float* G) -> int {
-        CUtensorMap tmF, tmA;
-        const uint64_t dF[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)B};
-        const uint64_t dA[4] = {(uint64_t)W, (uint64_t)H, 81, (uint64_t)B};
-        const uint64_t sF[3] = {(uint64_t)F.sh * 4, (uint64_t)F.sc * 4, (uint64_t)F.sn * 4};
-        const uint64_t sA[3] = {(uint64_t)A.sh * 4, (uint64_t)A.sc * 4, (uint64_t)A.sn * 4};
-        const uint32_t bF[4] = {(uint32_t)bwd::FW, (uint32_t)bwd::FH, (uint32_t)bwd::CK, 1};
-        const uint32_t bA[4] = {(uint32_t)bwd::TW, (uint32_t)bwd::TH, 81, 1};
-        const bool strides_ok = (W % 4 == 0) && F.sw == 1 && A.sw == 1 && F.sh > 0 && F.sc > 0 && A.sh > 0 && A.sc > 0 &&
-                                (B == 1 || (F.sn > 0 && A.sn > 0));
-        const bool tma = strides_ok && encode_tensor_map_4d(&tmF, F.p, dF, sF, bF) && encode_tensor_map_4d(&tmA, A.p, dA, sA, bA);
-        cudaError_t e;
-        if (tma) {
-            e = cudaFuncSetAttribute(corr81_bwd_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES);
-            if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
-            corr81_bwd_tile_kernel<true><<<grid, bwd::NT, bwd::SMEM_BYTES, s>>>(tmF, tmA, F, A, G, C, H, W, rc);
-        } else {
-            memset(&tmF, 0, sizeof(tmF)); memset(&tmA, 0, sizeof(tmA));
-            e = cudaFuncSetAttribute(corr81_bwd_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES);
-            if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
-            corr81_bwd_tile_kernel<false><<<grid, bwd::NT, bwd::SMEM_BYTES, s>>>(tmF, tmA, F, A, G, C, H, W, rc);
-        }
-        return check_launch();
+    const int nfirst = grad_first ? 1 : 0, nsecond = grad_second ? 1 : 0;
+    if ((long long)B * (nfirst + nsecond) > 65535) return FLDR_ERR_UNSUPPORTED;
+    dim3 grid((W + bwd::TW - 1) / bwd::TW, (H + bwd::TH - 1) / bwd::TH, B * (nfirst + nsecond));
+    CUtensorMap tmF1, tmF2, tmA;
+    const uint64_t dF[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)B};
+    const uint64_t dA[4] = {(uint64_t)W, (uint64_t)H, 81, (uint64_t)B};
+    const uint32_t bF[4] = {(uint32_t)bwd::FW, (uint32_t)bwd::FH, (uint32_t)bwd::CK, 1};
+    const uint32_t bA[4] = {(uint32_t)bwd::TW, (uint32_t)bwd::TH, 81, 1};
+    auto view_ok = [&](const View4& v) { return v.sw == 1 && v.sh > 0 && v.sc > 0 && (B == 1 || v.sn > 0); };
+    auto enc = [&](CUtensorMap* m, const View4& v, const uint64_t* d, const uint32_t* bx) {
+        const uint64_t sb[3] = {(uint64_t)v.sh * 4, (uint64_t)v.sc * 4, (uint64_t)(B == 1 && v.sn <= 0 ? (long long)d[2] * v.sc : v.sn) * 4};
+        return encode_tensor_map_4d(m, v.p, d, sb, bx);
     };
-    if (grad_first) {
-        if ((st = launch(v2, vg, grad_first)) != FLDR_OK) return st;
-    }
-    if (grad_second) {
-        float* g2 = static_cast<float*>(ws);
-        dim3 sgrid((unsigned)((HW + 255) / 256), 81, B);
-        corr81_bwd_shift_kernel<<<sgrid, 256, 0, s>>>(vg, g2, H, W);
-        if ((st = check_launch()) != FLDR_OK) return st;
-        View4 va;
-        va.p = g2; va.sn = 81 * HW; va.sc = HW; va.sh = W; va.sw = 1;
-        if ((st = launch(v1, va, grad_second)) != FLDR_OK) return st;
-    }
-    return FLDR_OK;
+    bool tma = (W % 4 == 0) && view_ok(v1) && view_ok(v2) && view_ok(vg);
+    // F of gradFirst is `second`, F of gradSecond is `first`
+    if (tma) tma = enc(&tmF1, v2, dF, bF) && enc(&tmF2, v1, dF, bF) && enc(&tmA, vg, dA, bA);
+    if (!tma) { memset(&tmF1, 0, sizeof(tmF1)); memset(&tmF2, 0, sizeof(tmF2)); memset(&tmA, 0, sizeof(tmA)); }
+    auto kern = tma ? corr81_bwd_tile_kernel<true> : corr81_bwd_tile_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES);
+    if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
+    kern<<<grid, bwd::NT, bwd::SMEM_BYTES, s>>>(tmF1, tmF2, tmA, v2, v1, vg, grad_first, grad_second, B, nfirst, C, H, W, rc);
+    return check_launch();
 }

@@ -56,8 +56,34 @@ def test_errors(cuda_lib):
     t = torch.full((1, 1), 0.5, device="cuda")
     with pytest.raises(TypeError):                      # a float32 temperature would silently change the arithmetic type
         Bl.occ_blend(lg, torch.ones(1, device="cuda"), t, x, x, x, x, x, x)
-    with pytest.raises(NotImplementedError):
-        Bl.occ_blend(lg.requires_grad_(True), torch.ones(1, dtype=torch.float64, device="cuda"), t, x, x, x, x, x, x)
+    with pytest.raises(NotImplementedError):             # occ_0 is a forward-only extra
+        Bl.occ_blend(lg.requires_grad_(True), torch.ones(1, dtype=torch.float64, device="cuda"), t, x, x, x, x, x, x, return_occ0=True)
+
+
+def test_gradients_vs_reference_lines_under_autograd(cuda_lib):
+    """Backward of the blend (training differentiates through fLDRnet.py:509-524: the logits, the splatted images, and T_param
+    when TOptimization is on) against autograd through the oracle's restatement of those lines."""
+    from oracle import blend_oracle as bo
+    from oracle import synth
+    Bl = _mod(cuda_lib)
+    N, C, H, W = 2, 3, 12, 20
+    imgs = [synth.image(N, C, H, W, seed=300 + k) for k in range(6)]
+    lg = synth.grad((N, 8, H, W), seed=310) * 2.0
+    t = torch.tensor([[0.5], [0.3]])
+    T = torch.full((1,), 0.8, dtype=torch.float64)
+    go = synth.grad((N, C, H, W), seed=311).double()
+    lr, Tr = lg.clone().requires_grad_(True), T.clone().requires_grad_(True)
+    ir = [im.clone().requires_grad_(True) for im in imgs]
+    oo, _ = bo.occ_blend(lr, Tr, t, *ir)
+    ref = torch.autograd.grad(oo, [lr, Tr] + ir, go)
+    ld, Td = lg.cuda().requires_grad_(True), T.cuda().requires_grad_(True)
+    idv = [im.cuda().requires_grad_(True) for im in imgs]
+    out = Bl.occ_blend(ld, Td, t.cuda(), *idv)
+    assert float((out.detach().cpu() - oo.detach()).abs().max()) <= 2e-14
+    got = torch.autograd.grad(out, [ld, Td] + idv, go.cuda())
+    for a, b, nm in zip(got, ref, ["logits", "T_param"] + [f"image{k}" for k in range(6)]):
+        assert a.dtype == b.dtype, nm
+        assert float((a.cpu().double() - b.double()).abs().max()) <= 1e-6 * max(1.0, float(b.abs().max())), nm
 
 
 def test_4k_vs_reference_operator_sequence(cuda_lib):

@@ -121,8 +121,20 @@ def test_leaky_relu_epilogue_and_concat_buffer(cuda_lib, B, C, H, W):
         assert_corr_close(same, plain.cpu(), scale, "slope 1 = plain correlation")
 
 
-def test_leaky_relu_entry_point_is_forward_only(cuda_lib):
+def test_leaky_relu_entry_point_gradients(cuda_lib):
+    """PWCNet.py:146-158 under autograd: leaky_relu(correlation) - fused forward, backward through the slope mask and the
+    correlation backward kernels - against autograd through the oracle."""
+    import torch.nn.functional as F
     Cm = _mod(cuda_lib)
-    f = torch.zeros(1, 8, 8, 8, device="cuda", requires_grad=True)
-    with pytest.raises(NotImplementedError):
-        Cm.FunctionCorrelationLeakyReLU(tensorFirst=f, tensorSecond=f)
+    B, C, H, W = 2, 24, 12, 20
+    f1, f2 = synth.features(B, C, H, W, seed=91), synth.features(B, C, H, W, seed=92)
+    go = synth.grad((B, 81, H, W), seed=93)
+    a, b = f1.clone().requires_grad_(True), f2.clone().requires_grad_(True)
+    ref = F.leaky_relu(co.correlation_fwd(a, b), 0.1)
+    g1, g2 = torch.autograd.grad(ref, [a, b], go)
+    ad, bd = f1.cuda().requires_grad_(True), f2.cuda().requires_grad_(True)
+    out = Cm.FunctionCorrelationLeakyReLU(tensorFirst=ad, tensorSecond=bd, negative_slope=0.1)
+    d1, d2 = torch.autograd.grad(out, [ad, bd], go.cuda())
+    assert float((d1.cpu() - g1).abs().max()) < 1e-5 and float((d2.cpu() - g2).abs().max()) < 1e-5
+    with pytest.raises(NotImplementedError):             # writing into a caller's concat buffer stays forward-only
+        Cm.FunctionCorrelationLeakyReLU(tensorFirst=ad, tensorSecond=bd, out=torch.empty(B, 90, H, W, device="cuda"))

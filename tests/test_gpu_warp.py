@@ -133,16 +133,62 @@ def test_gradients_vs_oracle_autograd(cuda_lib, conv, N, C, H, W, scale):
     _grad_close(gf2, gfo, "grad_flow only")
 
 
-def test_metric_is_forward_only_and_dtype_checked(cuda_lib):
+def test_dtype_checked(cuda_lib):
     Wp = _mod(cuda_lib)
     x = torch.zeros(1, 3, 8, 8, device="cuda", requires_grad=True)
     fl = torch.zeros(1, 2, 8, 8, device="cuda")
-    with pytest.raises(NotImplementedError):
-        Wp.splat_metric(x, x, fl, -1.9)
     with torch.no_grad():
         assert Wp.bwarp(x, fl).shape == (1, 3, 8, 8)
     with pytest.raises(TypeError):
         Wp.bwarp(x.detach().double(), fl)
+
+
+@pytest.mark.parametrize("N,C,H,W,scale,alpha_tensor", [(2, 3, 24, 40, 6.0, True), (1, 3, 17, 23, 2.0, False)])
+def test_metric_gradients_vs_oracle_autograd(cuda_lib, N, C, H, W, scale, alpha_tensor):
+    """Backward of z = mean_c(alpha * |ref - bwarp(src, flow)|) (fLDRnet.py:442-446 under autograd: training differentiates
+    through z_alpha, the frames and the flow) against torch's autograd through the oracle."""
+    Wp = _mod(cuda_lib)
+    ref = synth.image(N, C, H, W, seed=61)
+    src = synth.image(N, C, H, W, seed=62)
+    fl = synth.flow(N, H, W, "F1", seed=63) * scale
+    gz = synth.grad((N, 1, H, W), seed=64)
+    a0 = -1.894
+    rr, sr, fr = ref.clone().requires_grad_(True), src.clone().requires_grad_(True), fl.clone().requires_grad_(True)
+    ar = torch.tensor(a0, requires_grad=True)
+    zo = wo.warp_metric(rr, sr, fr, ar, cuda_semantics=True)
+    g_ref, g_src, g_fl, g_a = torch.autograd.grad(zo, [rr, sr, fr, ar], gz)
+    rd, sd, fd = ref.cuda().requires_grad_(True), src.cuda().requires_grad_(True), fl.cuda().requires_grad_(True)
+    ad = torch.tensor(a0, device="cuda", requires_grad=True) if alpha_tensor else a0
+    z = Wp.splat_metric(rd, sd, fd, ad)
+    assert float((z.detach().cpu() - zo.detach()).abs().max()) <= 4e-6
+    wrt = [rd, sd, fd] + ([ad] if alpha_tensor else [])
+    grads = torch.autograd.grad(z, wrt, gz.cuda())
+    _grad_close(grads[0], g_ref, "metric grad_ref")
+    _grad_close(grads[1], g_src, "metric grad_src")
+    _grad_close(grads[2], g_fl, "metric grad_flow")
+    if alpha_tensor:
+        assert abs(float(grads[3]) - float(g_a)) <= 1e-4 * max(1.0, abs(float(g_a)))
+
+
+def test_occlusion_aware_splat_entry_point(cuda_lib):
+    """fLDRnet.py:442-443 + 449 as one call: same result as metric + splat composed from the oracles, and differentiable."""
+    import fldr_vfi_b200.softSplat as S
+    from oracle import splat_oracle as so
+    Wp = _mod(cuda_lib)
+    N, C, H, W = 2, 3, 32, 48
+    x0, x1 = synth.image(N, C, H, W, seed=71), synth.image(N, C, H, W, seed=72)
+    f01 = synth.flow(N, H, W, "F1", seed=73) * 6
+    ft0 = synth.flow(N, H, W, "F1", seed=74) * 6
+    zo = wo.warp_metric(x0, x1, f01, -1.894, cuda_semantics=True)
+    yo = so.function_softsplat(x0, ft0, zo, "softmax")
+    with torch.no_grad():
+        y = Wp.occlusion_aware_splat(x0.cuda(), x1.cuda(), f01.cuda(), -1.894, ft0.cuda())
+    assert float((y.cpu() - yo).abs().max()) <= 1e-4
+    xd = x0.cuda().requires_grad_(True)
+    a = torch.tensor(-1.894, device="cuda", requires_grad=True)
+    yg = Wp.occlusion_aware_splat(xd, x1.cuda(), f01.cuda(), a, ft0.cuda())
+    gx, ga = torch.autograd.grad(yg.sum(), [xd, a])
+    assert gx.shape == xd.shape and torch.isfinite(gx).all() and torch.isfinite(ga)
 
 
 def test_4k_vs_torch_grid_sample_and_properties(cuda_lib):
