@@ -155,7 +155,7 @@ def test_metric_gradients_vs_oracle_autograd(cuda_lib, N, C, H, W, scale, alpha_
     a0 = -1.894
     rr, sr, fr = ref.clone().requires_grad_(True), src.clone().requires_grad_(True), fl.clone().requires_grad_(True)
     ar = torch.tensor(a0, requires_grad=True)
-    zo = wo.warp_metric(rr, sr, fr, ar, cuda_semantics=True)
+    zo = torch.mean(ar * torch.abs(rr - wo.bwarp(sr, fr, True, cuda_semantics=True)), dim=1, keepdim=True)     # fLDRnet.py:442-443
     g_ref, g_src, g_fl, g_a = torch.autograd.grad(zo, [rr, sr, fr, ar], gz)
     rd, sd, fd = ref.cuda().requires_grad_(True), src.cuda().requires_grad_(True), fl.cuda().requires_grad_(True)
     ad = torch.tensor(a0, device="cuda", requires_grad=True) if alpha_tensor else a0
