@@ -357,7 +357,11 @@ static int launch_fwd_tma(const View4& f1, const View4& f2, float* out, int B, i
 //   feeding 36 FFMA per channel into acc[8 channels][4 pixels].
 // ------------------------------------------------------------------------------------------------
 namespace bwd {
-constexpr int TW = 32, TH = 4, CK = 32, NT = 128;      // 2 CTAs per SM: one loads while the other computes
+#ifndef FLDR_CORR_BWD_CK
+#define FLDR_CORR_BWD_CK 16
+#endif
+constexpr int TW = 32, TH = 4, CK = FLDR_CORR_BWD_CK, NT = 128;      // CK = 16: 72 KB of shared memory, 3 CTAs per SM (measured 636 vs 734 us at CK = 32: the kernel is shared-memory-bandwidth bound, more warps hide more)
+constexpr int CPT = CK / 4;                             // channels per thread
 constexpr int FH = TH + 2 * kPad, FW = TW + 2 * kPad;
 constexpr int A_FLOATS = 81 * TH * TW, F_FLOATS = CK * FH * FW;
 constexpr int SMEM_BYTES = (A_FLOATS + F_FLOATS) * 4 + 16;          // 41472 + 61440 + mbarrier
@@ -365,7 +369,7 @@ constexpr int SMEM_BYTES = (A_FLOATS + F_FLOATS) * 4 + 16;          // 41472 + 6
 
 // acc[8 channels][4 pixels] += sum over the 81 displacements, operands in shared memory
 __device__ __forceinline__ void bwd_tile_compute(const float* __restrict__ sA, const float* __restrict__ sF, int pg, int row,
-                                                 int cg, float (&acc)[8][4]) {
+                                                 int cg, float (&acc)[bwd::CPT][4]) {
     using namespace bwd;
 #pragma unroll 1
     for (int p = 0; p < kD; ++p) {
@@ -376,8 +380,8 @@ __device__ __forceinline__ void bwd_tile_compute(const float* __restrict__ sA, c
             g[o][0] = g4.x; g[o][1] = g4.y; g[o][2] = g4.z; g[o][3] = g4.w;
         }
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
-            const float4* rp = reinterpret_cast<const float4*>(sF + ((cg * 8 + cc) * FH + row + p) * FW + pg * 4);
+        for (int cc = 0; cc < CPT; ++cc) {
+            const float4* rp = reinterpret_cast<const float4*>(sF + ((cg * CPT + cc) * FH + row + p) * FW + pg * 4);
             const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
             const float f[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
 #pragma unroll
@@ -395,7 +399,7 @@ __device__ __forceinline__ void bwd_tile_compute(const float* __restrict__ sA, c
 // the first version materialised in a workspace (one write + one read of 81*B*H*W floats, and a launch) is gone.
 // TMA: the unshifted A tile and every F chunk arrive as bulk tensor loads (zero fill outside the frame / beyond C).
 template <bool TMA>
-__global__ void __launch_bounds__(bwd::NT, 2)
+__global__ void __launch_bounds__(bwd::NT, bwd::CK == 32 ? 2 : 3)
 corr81_bwd_tile_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_constant__ CUtensorMap tmF2,
                        const __grid_constant__ CUtensorMap tmA, View4 F1, View4 F2, View4 A, float* __restrict__ G1,
                        float* __restrict__ G2, int B, int nfirst, int C, int H, int W, float rc) {
@@ -465,16 +469,16 @@ corr81_bwd_tile_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_co
             }
             __syncthreads();
         }
-        float acc[8][4];
+        float acc[CPT][4];
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc)
+        for (int cc = 0; cc < CPT; ++cc)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[cc][j] = 0.f;
         bwd_tile_compute(sA, sF, pg, row, cg, acc);
         if (y < H && x < W) {
 #pragma unroll
-            for (int cc = 0; cc < 8; ++cc) {
-                const int c = c0 + cg * 8 + cc;
+            for (int cc = 0; cc < CPT; ++cc) {
+                const int c = c0 + cg * CPT + cc;
                 if (c < C) {
                     float* gp = G + ((long long)b * C + c) * HW + (long long)y * W + x;
                     if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0) {
