@@ -23,6 +23,7 @@ SYMBOLS = {
     "fldr_splat_fwd": (ctypes.c_int, [ctypes.c_int, c_float_p, c_i64_p, c_float_p, c_i64_p, c_float_p, c_i64_p,
                                       c_float_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "fldr_splat_set_nonfinite_flag": (ctypes.c_int, [ctypes.c_void_p]),
     "fldr_splat_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 5),
     "fldr_splat_bwd": (ctypes.c_int, [ctypes.c_int, c_float_p, c_i64_p, c_float_p, c_i64_p, c_float_p, c_i64_p,
                                       c_float_p, c_float_p, c_float_p, c_i64_p, c_float_p, c_float_p, c_float_p,

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(fwd::NT) corr81_fwd_kernel(View4 f1, View4 f2,
     const float rc = 1.0f / (float)C;   // sum * (1/C): within 1 ulp of the reference's sum / C (exact for power-of-two C)
     const long long HW = (long long)H * W;
     float* ob = out + (long long)b * ep.out_sn + (long long)y * W + x;
-    const bool vec = ((W & 3) == 0) && (x + 3 < W) && ((ep.out_sn & 3) == 0);
+    const bool vec = ((W & 3) == 0) && (x + 3 < W) && ((ep.out_sn & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 #pragma unroll
     for (int d = 0; d < 3; ++d)
 #pragma unroll
@@ -530,7 +530,7 @@ static int corr81_fwd_impl(const float* first, const int64_t* first_strides, con
         const bool use16 = th_opt == 16;
         (void)tiles16;
         // float4 stores / reductions need 16-byte aligned samples
-        if ((ep.out_sn & 3) == 0) {
+        if ((ep.out_sn & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {      // float4 stores / reductions: 16-byte aligned base and samples
             st = use16 ? launch_fwd_tma<16>(v1, v2, out, B, C, H, W, s, &used, ep) : launch_fwd_tma<8>(v1, v2, out, B, C, H, W, s, &used, ep);
             if (st != FLDR_OK || used) return st;
         }

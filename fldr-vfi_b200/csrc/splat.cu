@@ -58,6 +58,17 @@ namespace fldr {
 // ------------------------------------------------------------------------------------------------
 constexpr int kSentinel = -(1 << 28);
 
+// Optional debug flag (fldr_splat_set_nonfinite_flag): the reference device-asserts on a non-finite target coordinate
+// (softSplat.py:25-26) and kills the context; here the pixel is skipped and, when a flag word is registered, that word is set
+// so a caller can find out (the wrapper polls it only in debug mode: reading it costs a synchronisation).
+__device__ unsigned* g_nonfinite_flag = nullptr;
+__device__ __forceinline__ void note_nonfinite(float X, float Y) {
+    if (!(fabsf(X) <= 3.0e38f && fabsf(Y) <= 3.0e38f)) {
+        unsigned* f = g_nonfinite_flag;
+        if (f) *f = 1u;
+    }
+}
+
 template <int PX> __device__ __forceinline__ void vstore(float* p, const float* t);
 template <> __device__ __forceinline__ void vstore<1>(float* p, const float* t) { __stcs(p, t[0]); }
 template <> __device__ __forceinline__ void vstore<4>(float* p, const float* t) {
@@ -144,6 +155,7 @@ __device__ __forceinline__ void scatter_rows(const View4& in, const View4& flow,
         const float X = xf + u, Y = (float)(yb + r) + v;
         const float fx0 = floorf(X), fy0 = floorf(Y);
         const bool ok = inb && fx0 >= -1.f && fx0 < (float)W && fy0 >= -1.f && fy0 < (float)H;   // false for NaN / inf
+        if (inb && !ok) note_nonfinite(X, Y);
         const int x0 = ok ? (int)fx0 : kSentinel;
         const int y0 = ok ? (int)fy0 : kSentinel;
         if (ok && acc.prefetch_rows() > 0) {
@@ -329,6 +341,7 @@ __global__ void __launch_bounds__(tile::TW, 6) splat_scatter_tile_kernel(const _
         const float fx0 = floorf(X), fy0 = floorf(Y);
         const float x1f = fx0 + 1.f, y1f = fy0 + 1.f;
         const bool pR = inb && fx0 >= -1.f && fx0 < Wf && fy0 >= -1.f && fy0 < Hf;   // false for NaN / inf (the reference asserts, 25-26)
+        if (inb && !pR) note_nonfinite(X, Y);
         const bool pT = pR && fy0 >= 0.f;                        // top corners in frame
         const bool pB = pR && fy0 < Hm1;                         // bottom corners in frame
         const int cx = (int)x1f;                                 // x0 + 1 = cell of the W corners (guard cell at 0)
@@ -652,6 +665,12 @@ static int plan_fwd(int mode, int N, int C, int H, int W, bool has_metric, FwdPl
 }  // namespace fldr
 
 using namespace fldr;
+
+extern "C" int fldr_splat_set_nonfinite_flag(unsigned int* device_flag) {
+    cudaError_t e = cudaMemcpyToSymbol(g_nonfinite_flag, &device_flag, sizeof(device_flag));
+    if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
+    return FLDR_OK;
+}
 
 extern "C" size_t fldr_splat_fwd_workspace_bytes(int mode, int N, int C, int H, int W) {
     FwdPlan p;

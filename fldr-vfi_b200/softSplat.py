@@ -12,6 +12,7 @@ kernel; no per-call regex templating (160-213); views are consumed through their
 non-finite flow skips the pixel instead of tripping a device assert (25-26).
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -40,7 +41,7 @@ class _device_of:
         self.prev = None
 
     def __enter__(self):
-        cur = torch.cuda.current_device()
+        cur = torch._C._cuda_getDevice()
         if cur != self.idx:
             self.prev = cur
             torch.cuda.set_device(self.idx)
@@ -51,8 +52,26 @@ class _device_of:
         return False
 
 
+_ws_cache = {}
+
+
 def _workspace(nbytes, device):
-    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+    """Scratch for one call.  One grow-only buffer per (device, stream) is kept and reused: kernels of successive calls on a
+    stream are ordered, so they can share it, and a 4K splat does not ask the allocator for 151 MB per call (calls issued on
+    different streams get different buffers)."""
+    nbytes = max(int(nbytes), 16)
+    if torch.cuda.is_current_stream_capturing():          # graph capture: the graph's private pool owns its scratch
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    key = (device.index, torch._C._cuda_getCurrentRawStream(device.index))
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = _ws_cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return buf
+
+
+def release_workspaces():
+    """Drop the cached scratch buffers (they are re-created on demand)."""
+    _ws_cache.clear()
 
 
 _ws_bytes_cache = {}
@@ -65,6 +84,20 @@ def _cached_ws_bytes(fn, *key):
     if v is None:
         v = _ws_bytes_cache[k] = int(fn(*key))
     return v
+
+
+_CHECK_FLOW = os.environ.get("FLDR_B200_CHECK_FLOW", "0") not in ("", "0")
+_flow_flags = {}
+
+
+def _flow_flag(device):
+    """Debug mode (FLDR_B200_CHECK_FLOW=1): the device word the splat kernels raise on a non-finite flow, one per device."""
+    f = _flow_flags.get(device.index)
+    if f is None:
+        f = _flow_flags[device.index] = torch.zeros(1, dtype=torch.int32, device=device)
+        with _device_of(f):
+            _lib.check(_lib.lib().fldr_splat_set_nonfinite_flag(ctypes.c_void_p(f.data_ptr())))
+    return f
 
 
 def _splat_forward(mode, tenInput, tenFlow, tenMetric, want_norm):
@@ -86,6 +119,12 @@ def _splat_forward(mode, tenInput, tenFlow, tenMetric, want_norm):
                                 _lib.strides(tenFlow), _lib.ptr(metric), None if metric is None else _lib.strides(metric),
                                 _lib.ptr(out), _lib.ptr(norm), N, C, H, W, _lib.ptr(ws), ws_bytes, _stream_ptr(dev))
     _lib.check(st)
+    if _CHECK_FLOW:
+        flag = _flow_flag(dev)
+        if int(flag.item()):                               # synchronises: debug mode only
+            flag.zero_()
+            raise RuntimeError("non-finite flow: the reference asserts isfinite on the target coordinates (softSplat.py:25-26); "
+                               "those pixels were skipped")
     return out, norm
 
 

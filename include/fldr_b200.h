@@ -100,6 +100,14 @@ int fldr_splat_fwd(int mode,
                    int N, int C, int H, int W,
                    void* ws, size_t ws_bytes, fldr_stream_t stream);
 
+/*
+ * Debug aid for the reference's device assert on non-finite flow (softSplat.py:25-26, which kills the CUDA context).  Here such
+ * a pixel is skipped; when a device word is registered with this call (per device; NULL unregisters), every forward splat
+ * that meets a non-finite target coordinate stores 1 into it.  The caller zeroes and reads the word (a synchronisation, so
+ * the Python wrapper only does it when FLDR_B200_CHECK_FLOW=1).
+ */
+int fldr_splat_set_nonfinite_flag(unsigned int* device_flag);
+
 size_t fldr_splat_bwd_workspace_bytes(int mode, int N, int C, int H, int W);
 
 /*

@@ -129,6 +129,31 @@ def test_nonfinite_flow_is_skipped(cuda_lib):
     assert torch.allclose(y, ref, atol=1e-6)
 
 
+def test_nonfinite_flow_raises_the_debug_flag(cuda_lib):
+    """The optional device word (fldr_splat_set_nonfinite_flag): set by a NaN / inf flow, untouched by a clean one; with
+    FLDR_B200_CHECK_FLOW=1 the wrapper polls it and raises where the reference device-asserts (softSplat.py:25-26)."""
+    import ctypes
+    S = _mods(cuda_lib)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    assert cuda_lib.fldr_splat_set_nonfinite_flag(ctypes.c_void_p(flag.data_ptr())) == 0
+    try:
+        x = synth.image(1, 3, 64, 96, seed=41).cuda()
+        fl = synth.flow(1, 64, 96, "F1", seed=42).cuda()
+        for big in (False, True):                       # the single cooperative launch and the tile scatter kernel
+            old = cuda_lib.fldr_get_option(b"splat_fused_max")
+            cuda_lib.fldr_set_option(b"splat_fused_max", 0 if big else old)
+            flag.zero_()
+            S.FunctionSoftsplat(x, fl, None, "softmax")
+            assert int(flag.item()) == 0
+            bad = fl.clone()
+            bad[0, 1, 5, 7] = float("inf")
+            S.FunctionSoftsplat(x, bad, None, "softmax")
+            assert int(flag.item()) == 1
+            cuda_lib.fldr_set_option(b"splat_fused_max", old)
+    finally:
+        assert cuda_lib.fldr_splat_set_nonfinite_flag(None) == 0
+
+
 def test_error_behaviour(cuda_lib):
     S = _mods(cuda_lib)
     x = torch.zeros(1, 3, 8, 8)
