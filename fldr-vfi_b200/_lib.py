@@ -84,6 +84,35 @@ def lib():
     return _lib
 
 
+_ext = None
+_ext_tried = False
+
+
+def ext():
+    """The thin torch C++ extension over the same C ABI (``_fldr_torch_ext*.so``, built by build_ext.py), or None when it
+    was not built - the ctypes binding above then serves every call (same library, same kernels, a few microseconds more
+    host time per call).  FLDR_B200_NO_EXT=1 forces the ctypes binding."""
+    global _ext, _ext_tried
+    if not _ext_tried:
+        _ext_tried = True
+        if os.environ.get("FLDR_B200_NO_EXT", "0") in ("", "0"):
+            import glob
+            import importlib.util
+            found = glob.glob(os.path.join(_HERE, "_fldr_torch_ext*.so"))
+            if found:
+                try:
+                    lib()                                   # libfldr_b200.so first: the extension links against it
+                    import torch  # noqa: F401  (libtorch / libcudart must be loaded before the extension)
+                    spec = importlib.util.spec_from_file_location("_fldr_torch_ext", found[0])
+                    mod = importlib.util.module_from_spec(spec)
+                    spec.loader.exec_module(mod)
+                    if mod.abi_version() == 1:
+                        _ext = mod
+                except Exception:                           # a stale / incompatible build: the ctypes binding serves the calls
+                    _ext = None
+    return _ext
+
+
 def check(status):
     if status != 0:
         l = lib()

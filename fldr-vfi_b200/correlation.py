@@ -25,6 +25,9 @@ def _corr_forward(first, second):
     assert (first.is_contiguous() == True)               # correlation.py:302
     assert (second.is_contiguous() == True)              # correlation.py:303
     assert first.shape == second.shape
+    ext = _lib.ext()
+    if ext is not None:
+        return ext.corr81_fwd(first, second)
     lib = _lib.lib()
     B, C, H, W = first.shape
     output = torch.empty((B, 81, H, W), dtype=torch.float32, device=first.device)
@@ -49,6 +52,10 @@ class _FunctionCorrelation(torch.autograd.Function):
         first, second = self.saved_tensors
         _check_cuda_f32("gradOutput", gradOutput)
         gradOutput = gradOutput.contiguous()                 # reference asserts contiguity (356); we accept any layout
+        ext = _lib.ext()
+        if ext is not None:
+            g1, g2 = ext.corr81_bwd(first, second, gradOutput, bool(self.needs_input_grad[0]), bool(self.needs_input_grad[1]))
+            return g1, g2
         lib = _lib.lib()
         B, C, H, W = first.shape
         gradFirst = torch.empty_like(first) if self.needs_input_grad[0] else None

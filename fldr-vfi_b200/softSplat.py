@@ -100,12 +100,28 @@ def _flow_flag(device):
     return f
 
 
+def _check_flow_flag(dev):
+    if _CHECK_FLOW:
+        flag = _flow_flag(dev)
+        if int(flag.item()):                               # synchronises: debug mode only
+            flag.zero_()
+            raise RuntimeError("non-finite flow: the reference asserts isfinite on the target coordinates (softSplat.py:25-26); "
+                               "those pixels were skipped")
+
+
 def _splat_forward(mode, tenInput, tenFlow, tenMetric, want_norm):
-    lib = _lib.lib()
     N, C, H, W = tenInput.shape
     assert tenFlow.shape[1] == 2                      # softSplat.py:227
     assert tenFlow.shape[0] == N and tenFlow.shape[2] == H and tenFlow.shape[3] == W   # 228-229
     dev = tenInput.device
+    if _CHECK_FLOW:
+        _flow_flag(dev)
+    ext = _lib.ext()
+    if ext is not None:
+        out, norm = ext.splat_fwd(mode, tenInput, tenFlow, tenMetric, bool(want_norm))
+        _check_flow_flag(dev)
+        return out, norm
+    lib = _lib.lib()
     out = torch.empty((N, C, H, W), dtype=torch.float32, device=dev)
     has_norm = mode in (1, 2, 3)
     norm = torch.empty((N, 1, H, W), dtype=torch.float32, device=dev) if (want_norm and has_norm) else None
@@ -119,16 +135,14 @@ def _splat_forward(mode, tenInput, tenFlow, tenMetric, want_norm):
                                 _lib.strides(tenFlow), _lib.ptr(metric), None if metric is None else _lib.strides(metric),
                                 _lib.ptr(out), _lib.ptr(norm), N, C, H, W, _lib.ptr(ws), ws_bytes, _stream_ptr(dev))
     _lib.check(st)
-    if _CHECK_FLOW:
-        flag = _flow_flag(dev)
-        if int(flag.item()):                               # synchronises: debug mode only
-            flag.zero_()
-            raise RuntimeError("non-finite flow: the reference asserts isfinite on the target coordinates (softSplat.py:25-26); "
-                               "those pixels were skipped")
+    _check_flow_flag(dev)
     return out, norm
 
 
 def _splat_backward(mode, tenInput, tenFlow, tenMetric, out, norm, gradOutput, need):
+    ext = _lib.ext()
+    if ext is not None:
+        return ext.splat_bwd(mode, tenInput, tenFlow, tenMetric, out, norm, gradOutput, bool(need[0]), bool(need[1]), bool(need[2]))
     lib = _lib.lib()
     N, C, H, W = tenInput.shape
     dev = tenInput.device
