@@ -88,10 +88,13 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> splat_bwd(int64_t mode, const at:
     if (metric.has_value()) m = metric->expand({N, 1, H, W});
     int64_t sm[4] = {0, 0, 0, 0};
     if (m.defined()) for (int i = 0; i < 4; ++i) sm[i] = m.stride(i);
+    const size_t ws_bytes = fldr_splat_bwd_workspace_bytes((int)mode, N, C, H, W);
+    at::Tensor ws = workspace(ws_bytes, in, stream);
     check(fldr_splat_bwd((int)mode, fptr(in), si.s, fptr(flow), sf.s, m.defined() ? fptr(m) : nullptr, m.defined() ? sm : nullptr,
                          out.has_value() ? fptr(*out) : nullptr, norm.has_value() ? fptr(*norm) : nullptr, fptr(grad_out), sg.s,
                          gin.defined() ? fptr_mut(gin) : nullptr, gfl.defined() ? fptr_mut(gfl) : nullptr,
-                         gme.defined() ? fptr_mut(gme) : nullptr, N, C, H, W, nullptr, 0, reinterpret_cast<fldr_stream_t>(stream)));
+                         gme.defined() ? fptr_mut(gme) : nullptr, N, C, H, W, ws.data_ptr(), (size_t)ws.numel(),
+                         reinterpret_cast<fldr_stream_t>(stream)));
     return std::make_tuple(gin, gfl, gme);
 }
 

@@ -23,7 +23,12 @@ def timeit(fn, iters=20, warm=3):
 
 shapes = [(1, 3, 2304, 4096, True, "F1"), (1, 3, 2304, 4096, True, "F2"), (1, 3, 2304, 4096, True, "F0"), (1, 48, 288, 512, False, "F1"),
           (1, 48, 144, 256, False, "F1"), (1, 48, 72, 128, False, "F1"), (32, 3, 512, 512, True, "F1"), (32, 3, 256, 256, True, "F1"),
-          (32, 48, 64, 64, False, "F1")]
+          (32, 48, 64, 64, False, "F1"), (1, 48, 36, 64, False, "F1"), (1, 48, 18, 32, False, "F1"), (32, 3, 64, 64, True, "F1"),
+          (32, 3, 128, 128, True, "F1")]
+if len(sys.argv) > 1 and sys.argv[1] == "4k":
+    shapes = [s for s in shapes if s[2] == 2304 and s[5] != "F0"] + [(32, 3, 512, 512, True, "F1")]
+if len(sys.argv) > 1 and sys.argv[1] == "small":
+    shapes = [s for s in shapes if s[2] * s[3] <= 25600]
 for (N, C, h, w, hm, reg) in shapes:
     x = (synth.features(N, C, h, w, seed=71) if C != 3 else synth.image(N, C, h, w, seed=71)).cuda()
     f = synth.flow(N, h, w, reg, seed=72)
