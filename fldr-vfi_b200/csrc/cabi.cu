@@ -27,9 +27,9 @@ int sm_count() {
 }  // namespace fldr
 
 namespace fldr {
-static const char* const kOptionNames[kOptCount] = {"splat_tma", "splat_fused_max", "corr_th", "splat_pf_rows"};
-static const char* const kOptionEnv[kOptCount] = {"FLDR_SPLAT_TMA", "FLDR_SPLAT_FUSED_MAX", "FLDR_CORR_TH", "FLDR_SPLAT_PF_ROWS"};
-static const int kOptionDefault[kOptCount] = {1, 40000, 0, 0};
+static const char* const kOptionNames[kOptCount] = {"splat_tma", "splat_fused_max", "corr_th", "splat_pf_rows", "corr_bwd_rows"};
+static const char* const kOptionEnv[kOptCount] = {"FLDR_SPLAT_TMA", "FLDR_SPLAT_FUSED_MAX", "FLDR_CORR_TH", "FLDR_SPLAT_PF_ROWS", "FLDR_CORR_BWD_ROWS"};
+static const int kOptionDefault[kOptCount] = {1, 40000, 0, 0, 1};
 static int g_options[kOptCount];
 static std::once_flag g_options_once;
 static void init_options() {
@@ -113,6 +113,14 @@ bool encode_tensor_map_4d(CUtensorMap* map, const float* base, const uint64_t di
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides_bytes, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT) {
+        // a thread that has only used the runtime API lazily (torch's autograd workers) may have no driver context bound yet:
+        // bind the primary context through the runtime and try once more, instead of silently losing the TMA path
+        cudaFree(nullptr);
+        r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides_bytes, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     return r == CUDA_SUCCESS;
 }
 

@@ -10,6 +10,8 @@
 //   corr81_bwd_tile_kernel  both gradients in one launch (gradSecond gathers the shifted gradOut tile itself)
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -494,6 +496,252 @@ corr81_bwd_tile_kernel(const __grid_constant__ CUtensorMap tmF1, const __grid_co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward, TMA path: three output rows per thread.
+// The tile kernel above moves 2.3 bytes of shared memory per FFMA (9 LDS.128 of A + 12 of F per 144 FFMA) and is bound by the
+// shared-memory pipe, not by the FMA pipe.  Here a thread owns 3 rows x 4 pixels x 4 channels: an F row segment (12 floats per
+// channel) loaded once serves the three output rows that see it under three different displacement rows p, so the same 12 + 27
+// LDS.128 feed 432 FFMA (1.5 B / FFMA - the forward kernel's ratio).  The thread walks s = 0..10: F row 3*rg + s, output row i
+// uses displacement row p = s - i.  A never sits in shared memory as a whole (81 planes x tile): its nine p-slices [9 o][TH][32]
+// stream through a 4-slot TMA ring in the order the walk consumes them (slices s, s-1, s-2 are live at step s).
+// gradSecond reads gradOut THROUGH the shift (correlation.py:200-236 with q = -p, r = -o): slice p is nine single-plane boxes,
+// plane 80 - (9p + o) at offset (x + o - 4, y + p - 4); the TMA unit's zero fill outside the frame is the frame mask.
+// ------------------------------------------------------------------------------------------------
+namespace bwr {
+constexpr int TW = 32, TH = 6, CK = 32, NT = 128, NRG = TH / 3;
+constexpr int FW = TW + 2 * kPad, FROWS = TH + 2 * kPad;            // F rows a tile needs (14)
+constexpr int FROW = CK * FW;                       // floats of one F row slot: [CK][40]
+constexpr int NF = 7;                               // F-row ring: rows s .. s+3 are live at step s, three more are in flight
+constexpr int AW2 = TW + 2 * kPad;                  // gradSecond: slice rows hold the aligned 40-column box around the tile
+constexpr int PP2 = 256;                            // gradSecond: plane pitch inside a slice (6 x 40 floats padded to 1024 B: a TMA destination is 128-byte aligned)
+constexpr int SLICE = kD * PP2;                     // floats reserved per p-slice (gradFirst uses 9 * TH * 32 of them)
+constexpr int RING = 4;                             // A-slice ring: slices s-2 .. s are live at step s
+constexpr int STEPS = kD + 2;
+constexpr int SMEM_BYTES = (NF * FROW + RING * SLICE) * 4 + 128;   // 35 840 + 36 864 + barriers: three CTAs per SM
+constexpr int CTAS_PER_SM = 3;
+}  // namespace bwr
+
+// four consecutive floats starting OFF floats after a 16-byte aligned shared-memory address (OFF known at compile time):
+// one LDS.128 when aligned, LDS.64 x2 or LDS.32 + LDS.64 + LDS.32 otherwise - 4 wavefronts in every case
+template <int OFF>
+__device__ __forceinline__ void lds4_at(const float* base, float (&v)[4]) {
+    const float* p = base + OFF;
+    if (OFF % 4 == 0) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if (OFF % 2 == 0) {
+        const float2 a = *reinterpret_cast<const float2*>(p), c = *reinterpret_cast<const float2*>(p + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = c.x; v[3] = c.y;
+    } else {
+        const float2 m = *reinterpret_cast<const float2*>(p + 1);
+        v[0] = p[0]; v[1] = m.x; v[2] = m.y; v[3] = p[3];
+    }
+}
+
+// one step of the walk: F row (3 rg + s) against the displacement rows p = s - i of output rows i = 0, 1, 2
+// ROWS: which of the three output rows have a displacement row in range at this step (bit i); known at compile time so that a
+// step is ONE basic block - the loads of a row's A values are scheduled above the previous row's FFMAs
+template <bool SECOND, int ROWS>
+__device__ __forceinline__ void bwd_rows_step(float (&acc)[4][3][4], const float* frow, const float* ring, int slice0, int s, int goff) {
+    using namespace bwr;
+    constexpr int AW = SECOND ? AW2 : TW;             // row pitch of a slice in shared memory
+    constexpr int PP = SECOND ? PP2 : TH * TW;        // plane pitch
+    float f[4][12];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const float4* rp = reinterpret_cast<const float4*>(frow + cc * FW);
+        const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
+        f[cc][0] = r0.x; f[cc][1] = r0.y; f[cc][2] = r0.z; f[cc][3] = r0.w;
+        f[cc][4] = r1.x; f[cc][5] = r1.y; f[cc][6] = r1.z; f[cc][7] = r1.w;
+        f[cc][8] = r2.x; f[cc][9] = r2.y; f[cc][10] = r2.z; f[cc][11] = r2.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int p = s - i;
+        if (ROWS >> i & 1) {
+            const float* ga = ring + ((slice0 + p) & (RING - 1)) * SLICE + goff + i * AW;
+            float g[kD][4];
+            if (!SECOND) {
+#pragma unroll
+                for (int o = 0; o < kD; ++o) lds4_at<0>(ga + o * PP, g[o]);
+            } else {
+                lds4_at<0>(ga + 0 * PP, g[0]); lds4_at<1>(ga + 1 * PP, g[1]); lds4_at<2>(ga + 2 * PP, g[2]);
+                lds4_at<3>(ga + 3 * PP, g[3]); lds4_at<4>(ga + 4 * PP, g[4]); lds4_at<5>(ga + 5 * PP, g[5]);
+                lds4_at<6>(ga + 6 * PP, g[6]); lds4_at<7>(ga + 7 * PP, g[7]); lds4_at<8>(ga + 8 * PP, g[8]);
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                for (int o = 0; o < kD; ++o)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[cc][i][k] = fmaf(g[o][k], f[cc][k + o], acc[cc][i][k]);
+        }
+    }
+}
+
+// Persistent CTAs (three per SM) loop over (tile, gradient) items; both operands stream through shared-memory rings that run on
+// across chunk and tile boundaries, so a CTA never sits through a load prologue:
+//   A: the nine p-slices of gradOut, 4 slots (slices s-2 .. s are live at step s);
+//   F: the fourteen halo rows of the CK-channel chunk, [CK][40] each, 7 slots (rows s .. s+3 are live at step s).
+// Thread 0 refills after every step whatever slots the step just retired.
+template <bool SECOND>
+__global__ void __launch_bounds__(bwr::NT, bwr::CTAS_PER_SM)
+corr81_bwd_rows_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmA, float* __restrict__ G, int B, int C,
+                       int H, int W, int tilesX, int tilesY, float rc) {
+    using namespace bwr;
+    extern __shared__ __align__(128) float smem_f[];
+    float* sF = smem_f;                               // [NF][CK][FW]
+    float* ring = smem_f + NF * FROW;                 // [RING][9][TH][32 or 40 (+ pad)]
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(smem_f + NF * FROW + RING * SLICE);
+    uint64_t* fullF = fullA + RING;
+    const int tid = threadIdx.x;
+    // a warp holds one row group: the unaligned 4- and 8-byte loads of gradSecond then touch 8 distinct, 16-byte spaced addresses
+    // (conflict-free, the four channel groups of the warp broadcast)
+    const int pg = tid & 7, w = tid >> 5, rg = w % NRG, cg = (w / NRG) * 4 + ((tid >> 3) & 3);
+    const int nchunks = (C + CK - 1) / CK;
+    const int nitems = tilesX * tilesY * B;
+    const int my_items = ((int)blockIdx.x < nitems) ? (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int units = my_items * nchunks;             // (item, chunk) pairs of this CTA
+    // item k of this CTA -> gradient, sample, tile origin
+    auto decode = [&](int k, int& b, int& x0t, int& y0t) {
+        int id = blockIdx.x + k * gridDim.x;
+        b = id / (tilesX * tilesY);
+        id -= b * (tilesX * tilesY);
+        y0t = (id / tilesX) * TH;
+        x0t = (id % tilesX) * TW;
+    };
+    if (tid == 0) {
+        for (int i = 0; i < RING; ++i) mbar_init(&fullA[i], 1);
+        for (int i = 0; i < NF; ++i) mbar_init(&fullF[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    // ---- producer state (shared memory, one writer at a time): cursors over the global slice index a = unit * 9 + p and the
+    // global row index r = unit * 14 + fr.  There is no producer thread and no CTA barrier: the LAST warp to finish a step
+    // refills what that step retired (the last finisher of step t+1 cannot precede the last finisher of step t, who refills
+    // before it moves on, so refills happen in step order; a warp can run at most three steps ahead of the slowest - step t+4
+    // needs the F row that the refill after step t issues - hence four arrival counters).
+    struct Cursor { int idx, k, j, q, b, x0t, y0t; };       // q = p (slices) or fr (rows) inside the unit
+    __shared__ Cursor curA, curF;
+    __shared__ int cnt[4];
+    const int total_a = units * kD, total_f = units * FROWS;
+    auto cursor_item = [&](Cursor& c) {
+        int b, x0t, y0t;
+        decode(c.k, b, x0t, y0t);
+        c.b = b; c.x0t = x0t; c.y0t = y0t;
+    };
+    auto issue_a = [&]() {                             // next slice
+        Cursor c = curA;
+        const int slot = c.idx & (RING - 1), p = c.q;
+        float* dst = ring + slot * SLICE;
+        if (!SECOND) {
+            mbar_arrive_expect_tx(&fullA[slot], kD * TH * TW * 4);
+            tma_load_4d(dst, &tmA, &fullA[slot], c.x0t, c.y0t, p * kD, c.b);
+        } else {
+            // plane 80 - (9p + o) shifted by (o - 4, p - 4): the box starts at the 16-byte aligned column x0t - 4 (a tensor-map
+            // coordinate of the innermost dimension must be a multiple of 16 bytes); the x shift is applied when the slice is read
+            mbar_arrive_expect_tx(&fullA[slot], kD * TH * AW2 * 4);
+#pragma unroll
+            for (int o = 0; o < kD; ++o)
+                tma_load_4d(dst + o * PP2, &tmA, &fullA[slot], c.x0t - kPad, c.y0t + p - kPad, 80 - (p * kD + o), c.b);
+        }
+        ++c.idx;
+        if (++c.q == kD) {
+            c.q = 0;
+            if (++c.j == nchunks) { c.j = 0; ++c.k; if (c.k < my_items) cursor_item(c); }
+        }
+        curA = c;
+    };
+    auto issue_f = [&]() {                             // next row
+        Cursor c = curF;
+        const int slot = c.idx % NF;
+        mbar_arrive_expect_tx(&fullF[slot], FROW * 4);
+        tma_load_4d(sF + slot * FROW, &tmF, &fullF[slot], c.x0t - kPad, c.y0t - kPad + c.q, c.j * CK, c.b);
+        ++c.idx;
+        if (++c.q == FROWS) {
+            c.q = 0;
+            if (++c.j == nchunks) { c.j = 0; ++c.k; if (c.k < my_items) cursor_item(c); }
+        }
+        curF = c;
+    };
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) cnt[i] = 0;
+        Cursor c = {0, 0, 0, 0, 0, 0, 0};
+        if (my_items > 0) cursor_item(c);
+        curA = c; curF = c;
+        while (curA.idx < RING && curA.idx < total_a) issue_a();
+        while (curF.idx < NF && curF.idx < total_f) issue_f();
+    }
+    __syncthreads();
+    const long long HW = (long long)H * W;
+    const int goff = (rg * 3) * (SECOND ? AW2 : TW) + pg * 4;
+    int u = 0;
+    for (int k = 0; k < my_items; ++k) {
+        int b, x0t, y0t;
+        decode(k, b, x0t, y0t);
+        for (int j = 0; j < nchunks; ++j, ++u) {
+            float acc[4][3][4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[cc][i][q] = 0.f;
+            // one step: wait for what it consumes, compute, retire
+            auto step = [&](int s, auto rows_tag) {
+                constexpr int ROWS = decltype(rows_tag)::value;
+                if (s < kD) {
+                    const int a = u * kD + s;
+                    mbar_wait(&fullA[a & (RING - 1)], (uint32_t)((a / RING) & 1));
+                }
+                {   // F rows up to s + 3 have landed (rows 0..3 before the first step)
+                    const int r1 = u * FROWS + min(s + 3, FROWS - 1);
+                    for (int r = (s == 0 ? u * FROWS : r1); r <= r1; ++r) mbar_wait(&fullF[r % NF], (uint32_t)((r / NF) & 1));
+                }
+                const float* frow = sF + ((u * FROWS + rg * 3 + s) % NF) * FROW + (cg * 4) * FW + pg * 4;
+                bwd_rows_step<SECOND, ROWS>(acc, frow, ring, u * kD, s, goff);
+                // this step's retirements: slice s - 2, F row s (everything after the last step); the last warp out refills
+                __syncwarp();
+                if ((tid & 31) == 0) {
+                    const int t = u * STEPS + s;
+                    if (atomicAdd(&cnt[t & 3], 1) == NT / 32 - 1) {
+                        cnt[t & 3] = 0;
+                        __threadfence_block();
+                        const int dead_a = u * kD + min(kD, max(0, s - 1));
+                        const int dead_f = u * FROWS + (s < STEPS - 1 ? s + 1 : FROWS);
+                        fence_proxy_async();           // generic-proxy reads of the retired slots before the async-proxy refills
+                        while (curA.idx < total_a && curA.idx - RING < dead_a) issue_a();
+                        while (curF.idx < total_f && curF.idx - NF < dead_f) issue_f();
+                    }
+                }
+                __syncwarp();
+            };
+            step(0, std::integral_constant<int, 1>());
+            step(1, std::integral_constant<int, 3>());
+#pragma unroll 1
+            for (int s = 2; s < kD; ++s) step(s, std::integral_constant<int, 7>());
+            step(kD, std::integral_constant<int, 6>());
+            step(kD + 1, std::integral_constant<int, 4>());
+            const int x = x0t + pg * 4;
+            if (x < W) {                                // W % 4 == 0 on this path
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c = j * CK + cg * 4 + cc;
+                    if (c < C) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const int y = y0t + rg * 3 + i;
+                            if (y < H)
+                                __stcs(reinterpret_cast<float4*>(G + ((long long)b * C + c) * HW + (long long)y * W + x),
+                                       make_float4(acc[cc][i][0] * rc, acc[cc][i][1] * rc, acc[cc][i][2] * rc, acc[cc][i][3] * rc));
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 static int check_corr_args(int B, int C, int H, int W) {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return FLDR_ERR_INVALID_ARGUMENT;
     if ((long long)H * W * 81 >= (1ll << 31) || B > 65535) return FLDR_ERR_UNSUPPORTED;
@@ -591,6 +839,38 @@ extern "C" int fldr_corr81_bwd(const float* first, const int64_t* first_strides,
     // F of gradFirst is `second`, F of gradSecond is `first`
     if (tma) tma = enc(&tmF1, v2, dF, bF) && enc(&tmF2, v1, dF, bF) && enc(&tmA, vg, dA, bA);
     if (!tma) { memset(&tmF1, 0, sizeof(tmF1)); memset(&tmF2, 0, sizeof(tmF2)); memset(&tmA, 0, sizeof(tmA)); }
+    const bool g_ok = (!grad_first || (reinterpret_cast<uintptr_t>(grad_first) & 15) == 0) && (!grad_second || (reinterpret_cast<uintptr_t>(grad_second) & 15) == 0);
+    // measured (profiles/r2_training_shapes_fwd_bwd.txt): the three-row kernel wins where one chunk holds all channels (C <= 32:
+    // 526 vs 626 us at 64x32x128x128); with more chunks it re-streams gradOut per chunk and ties with the tile kernel (316 vs 304 us
+    // at 64x64x64x64), which stays in charge there.  "corr_bwd_rows" = 2 forces it for every C.
+    const int rows_opt = get_option(kOptCorrBwdRows);
+    if (tma && g_ok && (rows_opt == 2 || (rows_opt == 1 && C <= bwr::CK))) {
+        CUtensorMap tmR1, tmR2, tmA9, tmA1;
+        const uint32_t bFr[4] = {(uint32_t)bwr::FW, 1, (uint32_t)bwr::CK, 1};
+        const uint32_t bA9[4] = {(uint32_t)bwr::TW, (uint32_t)bwr::TH, 9, 1};
+        const uint32_t bA1[4] = {(uint32_t)bwr::AW2, (uint32_t)bwr::TH, 1, 1};
+        if (enc(&tmR1, v2, dF, bFr) && enc(&tmR2, v1, dF, bFr) && enc(&tmA9, vg, dA, bA9) && enc(&tmA1, vg, dA, bA1)) {
+            static unsigned char attr_done[64];
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (dev < 0 || dev >= 64) dev = 0;
+            if (!__atomic_load_n(&attr_done[dev], __ATOMIC_ACQUIRE)) {
+                cudaError_t e = cudaFuncSetAttribute(corr81_bwd_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwr::SMEM_BYTES);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(corr81_bwd_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwr::SMEM_BYTES);
+                if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
+                __atomic_store_n(&attr_done[dev], 1, __ATOMIC_RELEASE);
+            }
+            const int tilesX = (W + bwr::TW - 1) / bwr::TW, tilesY = (H + bwr::TH - 1) / bwr::TH;
+            const long long nitems = (long long)tilesX * tilesY * B;
+            if (nitems >= (1ll << 30)) return FLDR_ERR_UNSUPPORTED;
+            const long long slots = (long long)bwr::CTAS_PER_SM * sm_count();
+            const int gridp = (int)(nitems < slots ? nitems : slots);
+            // one persistent launch per gradient (F of gradFirst is `second`, F of gradSecond is `first`)
+            if (grad_first) corr81_bwd_rows_kernel<false><<<gridp, bwr::NT, bwr::SMEM_BYTES, s>>>(tmR1, tmA9, grad_first, B, C, H, W, tilesX, tilesY, rc);
+            if (grad_second) corr81_bwd_rows_kernel<true><<<gridp, bwr::NT, bwr::SMEM_BYTES, s>>>(tmR2, tmA1, grad_second, B, C, H, W, tilesX, tilesY, rc);
+            return check_launch();
+        }
+    }
     auto kern = tma ? corr81_bwd_tile_kernel<true> : corr81_bwd_tile_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_BYTES);
     if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }

@@ -249,7 +249,10 @@ __global__ void __launch_bounds__(128, FLDR_SCATTER_MIN_CTAS) splat_scatter_merg
 // are the same memory cell, and the guard cells of the row pitch remove every x test from the reductions.
 // ------------------------------------------------------------------------------------------------
 namespace tile {
-constexpr int R = 8, TW = 128, PLANES = 6;
+#ifndef FLDR_TILE_R
+#define FLDR_TILE_R 8
+#endif
+constexpr int R = FLDR_TILE_R, TW = 128, PLANES = 6;
 constexpr int kSent = -(1 << 30);             // "no cell": stays negative after + 1
 }  // namespace tile
 

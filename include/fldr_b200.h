@@ -72,6 +72,8 @@ int fldr_last_cuda_error(void);
  *                    run zero + scatter + normalise as ONE cooperative launch; 0 disables
  *   "corr_th"        tile height of the correlation forward kernel: 0 automatic, 8 or 16 forced
  *   "splat_pf_rows"  accumulator rows prefetched into L2 ahead of the scatter (0 = default 4, negative = off)
+ *   "corr_bwd_rows"  1 (default): correlation backward with three output rows per thread and gradOut streamed through a TMA
+ *                    ring when the views allow it and C <= 32; 2 = for every C; 0 = always the 4-row tile kernel
  * Results are identical (within the summation-order tolerance) for every setting.
  */
 int fldr_set_option(const char* name, int value);

@@ -95,6 +95,51 @@ def test_native_4k_level_properties_and_crop(cuda_lib):
     assert_corr_close(a, co.correlation_fwd(f1, f2), co.correlation_fwd(f1.abs(), f2.abs()), "native level 2 vs oracle")
 
 
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 272, 512), (2, 96, 136, 256), (2, 128, 68, 128), (2, 196, 34, 64)])
+def test_native_4k_pyramid_levels_vs_oracle(cuda_lib, B, C, H, W):
+    """cfg2-native levels 3..6 at their literal sizes (level 2, C = 32, is the test above): the tile scheduling of C = 64 / 96 and the
+    channel-split path of C = 128 / 196, forward against the oracle at full size."""
+    Cm = _mod(cuda_lib)
+    f1 = synth.features(B, C, H, W, seed=63)
+    f2 = synth.features(B, C, H, W, seed=64)
+    with torch.no_grad():
+        out = Cm.FunctionCorrelation(tensorFirst=f1.cuda(), tensorSecond=f2.cuda())
+    assert_corr_close(out, co.correlation_fwd(f1, f2), co.correlation_fwd(f1.abs(), f2.abs()), f"native level C={C}")
+
+
+@pytest.mark.parametrize("B,C,H,W", [(64, 32, 128, 128), (64, 64, 64, 64), (64, 96, 32, 32), (64, 196, 8, 8)])
+def test_cfg5_training_shapes_fwd_bwd(cuda_lib, B, C, H, W):
+    """BASELINE configs[4] at the literal batch (B = 64 = 32 crops x 2 directions): the GPU runs the whole batch, forward and both
+    gradients; the oracle checks samples 0, 31 and 63 (samples are independent, correlation.py:365,385 launches them one by one)."""
+    Cm = _mod(cuda_lib)
+    f1 = synth.features(B, C, H, W, seed=65)
+    f2 = synth.features(B, C, H, W, seed=66)
+    gout = synth.grad((B, 81, H, W), seed=67)
+    f1d, f2d = f1.cuda().requires_grad_(True), f2.cuda().requires_grad_(True)
+    out = Cm.FunctionCorrelation(tensorFirst=f1d, tensorSecond=f2d)
+    g1, g2 = torch.autograd.grad(out, [f1d, f2d], gout.cuda())
+    for b in (0, 31, 63):
+        sl = slice(b, b + 1)
+        a, c, g = f1[sl], f2[sl], gout[sl]
+        assert_corr_close(out[sl], co.correlation_fwd(a, c), co.correlation_fwd(a.abs(), c.abs()), f"cfg5 C={C} sample {b} fwd")
+        assert_corr_close(g1[sl], co.correlation_grad_first(c, g), co.correlation_grad_first(c.abs(), g.abs()), f"cfg5 C={C} sample {b} gradFirst")
+        assert_corr_close(g2[sl], co.correlation_grad_second(a, g), co.correlation_grad_second(a.abs(), g.abs()), f"cfg5 C={C} sample {b} gradSecond")
+
+
+@pytest.mark.parametrize("rows", [0, 2])
+def test_backward_kernels_agree(cuda_lib, rows):
+    """Both backward kernels (three-rows-per-thread TMA ring, 4-row tile) against the oracle on a ragged multi-chunk shape."""
+    Cm = _mod(cuda_lib)
+    old = cuda_lib.fldr_get_option(b"corr_bwd_rows")
+    cuda_lib.fldr_set_option(b"corr_bwd_rows", rows)
+    try:
+        for (B, C, H, W) in [(2, 70, 13, 36), (1, 32, 7, 8), (3, 33, 19, 44)]:
+            _check(Cm, synth.features(B, C, H, W, seed=21), synth.features(B, C, H, W, seed=22), synth.grad((B, 81, H, W), seed=23),
+                   f"bwd rows={rows} B{B} C{C} {H}x{W}")
+    finally:
+        cuda_lib.fldr_set_option(b"corr_bwd_rows", old)
+
+
 # ---------------------------------------------------------------- next row (SURVEY 8f rank 3): fused leaky-relu + concat placement
 @pytest.mark.parametrize("B,C,H,W", [(2, 32, 24, 40), (1, 40, 9, 11), (2, 196, 5, 8), (2, 64, 72, 128), (1, 16, 17, 24)])
 def test_leaky_relu_epilogue_and_concat_buffer(cuda_lib, B, C, H, W):
