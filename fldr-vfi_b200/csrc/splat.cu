@@ -538,10 +538,15 @@ __global__ void __launch_bounds__(bwdp::NT, MINB) splat_bwd_prep_kernel(View4 go
                                                                   float4* __restrict__ G, SplatGeom g, int QB, int need_c) {
     constexpr int PX = VEC ? 4 : 1;
     const int P = g.W + 2;
-    const int yp = blockIdx.y;                              // padded row: 0 and H + 1 are the zero border
+    // threads are laid over the (padded row, pixel group) pairs of a plane in one flat index: narrow frames (the coarse training
+    // levels are 64 / 32 / 16 pixels wide) still fill their CTAs
+    const int gpr = (P + PX - 1) / PX;                      // pixel groups per padded row
+    const int flat = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yp = flat / gpr;                              // padded row: 0 and H + 1 are the zero border
+    if (yp > g.H + 1) return;
     const int q = blockIdx.z % QB, n = blockIdx.z / QB;
     float4* grow = G + ((size_t)(n * QB + q) * (g.H + 2) + yp) * P;
-    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
+    const int x = (flat - yp * gpr) * PX;
     if (yp == 0 || yp == g.H + 1) {
         for (int k = 0; k < PX; ++k)
             if (x + k < P) grow[x + k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1016,9 +1021,9 @@ extern "C" int fldr_splat_bwd(int mode, const float* in, const int64_t* in_strid
     {
         const bool vec = (W % 4 == 0) && vgo.sw == 1 && (vgo.sh % 4) == 0 && (vgo.sc % 4) == 0 && (vgo.sn % 4) == 0 && aligned16(vgo.p) &&
                          (!out || aligned16(out)) && (!norm || aligned16(norm));
-        const int cells = vec ? (W + 2 + 3) / 4 : W + 2;
-        const int bx = cells >= bwdp::NT ? bwdp::NT : ((cells + 31) / 32) * 32;
-        const dim3 grid((cells + bx - 1) / bx, H + 2, N * QB);
+        const long long cells = (long long)(vec ? (W + 2 + 3) / 4 : W + 2) * (H + 2);      // (row, pixel group) pairs of a plane
+        const int bx = bwdp::NT;
+        const dim3 grid((unsigned)((cells + bx - 1) / bx), 1, N * QB);
         if (vec) splat_bwd_prep_kernel<true, 8><<<grid, bx, 0, s>>>(vgo, out, norm, G, g, QB, need_c);
         else splat_bwd_prep_kernel<false, 4><<<grid, bx, 0, s>>>(vgo, out, norm, G, g, QB, need_c);
         if ((st = check_launch()) != FLDR_OK) return st;
