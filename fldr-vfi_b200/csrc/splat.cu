@@ -396,325 +396,6 @@ __global__ void __launch_bounds__(tile::TW, 6) splat_scatter_tile_kernel(const _
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tile-owner path (image splats whose whole-frame accumulator would not fit the L2): no global accumulator at all.
-// A persistent CTA OWNS one target tile (th rows x 128 columns) at a time and keeps that tile's accumulator in a private,
-// L2-resident scratch of th x 130 float4 cells (2 x 148 CTAs x 75 KB = 22 MB, reused tile after tile, never written back to
-// DRAM while it is hot).  The CTA scatters every source tile (8 rows x 32 columns, one warp) whose targets can reach its tile -
-// found through a bounding-box table a pre-pass builds from the flow (one box per source tile, one per 8 x 8 super-tile) - with
-// the same merged-reduction walk as the kernels above, keeping only the corners that fall inside its tile; then it normalises its
-// tile straight into the output and re-zeroes the scratch.  Every (pixel, corner) contribution has exactly one owner, nothing
-// is shared between CTAs, so there is no inter-CTA synchronisation, no memset, no accumulator round trip through DRAM:
-// DRAM traffic = inputs + flow once more (pre-pass) + outputs.
-// The price is examination: a source tile whose box straddles a tile border is walked by every owner it touches (2.2 owners per
-// source tile for the smooth regime F1; rows that miss the tile cost a flow load and ~20 instructions).  Rough flow (iid +-64 px
-// makes every box span ~12 target tiles) is detected from the boxes and handed to the three-pass path by a device-side verdict.
-// ------------------------------------------------------------------------------------------------
-namespace own {
-constexpr int SW = 32, SH = 8;          // source tile: one warp wide, 8 rows
-constexpr int TW = 128;                 // target tile width (its height th is chosen per call)
-constexpr int SUP = 8;                  // super-tile: 8 x 8 source tiles
-constexpr int NT = 512;
-constexpr int LIST = 1024;
-constexpr int P = TW + 2;               // scratch row pitch in cells (one guard cell either side)
-constexpr int kEmptyLo = 0x7fffffff, kEmptyHi = (int)0x80000000;
-struct Geom {
-    int N, H, W;
-    int stx, sty;        // source tiles per row / column of a frame
-    int supx, supy;      // super-tiles
-    int ttx, tty, th;    // target tiles, target tile height
-};
-}  // namespace own
-
-// Pre-pass: bounding box of the NW-corner coordinates (x0, y0) = floor(p + f) of every source tile's in-frame pixels, their union
-// per super-tile, and per super-tile the number of (source tile, target tile) pairs to examine.  grid (supx, supy, N) x 512.
-__global__ void __launch_bounds__(own::NT) splat_bbox_kernel(View4 flow, int4* __restrict__ fine, int4* __restrict__ coarse,
-                                                             int2* __restrict__ amp, own::Geom g) {
-    using namespace own;
-    __shared__ int s_box[4], s_amp[2];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = blockIdx.z;
-    if (tid == 0) { s_box[0] = kEmptyLo; s_box[1] = kEmptyHi; s_box[2] = kEmptyLo; s_box[3] = kEmptyHi; s_amp[0] = 0; s_amp[1] = 0; }
-    __syncthreads();
-    const float Wf = (float)g.W, Hf = (float)g.H;
-    int ux0 = kEmptyLo, ux1 = kEmptyHi, uy0 = kEmptyLo, uy1 = kEmptyHi, pairs = 0, live = 0;
-    for (int t = warp; t < SUP * SUP; t += NT / 32) {
-        const int sx = blockIdx.x * SUP + (t % SUP), sy = blockIdx.y * SUP + (t / SUP);
-        if (sx >= g.stx || sy >= g.sty) continue;                       // warp-uniform
-        const int x = sx * SW + lane;
-        int bx0 = kEmptyLo, bx1 = kEmptyHi, by0 = kEmptyLo, by1 = kEmptyHi;
-        if (x < g.W) {
-            const float* fu = flow.p + n * flow.sn + (long long)(sy * SH) * flow.sh + (long long)x * flow.sw;
-            const int rows = min(SH, g.H - sy * SH);
-            float u[SH], v[SH];
-#pragma unroll
-            for (int r = 0; r < SH; ++r)
-                if (r < rows) { u[r] = __ldg(fu + (long long)r * flow.sh); v[r] = __ldg(fu + flow.sc + (long long)r * flow.sh); }
-#pragma unroll
-            for (int r = 0; r < SH; ++r)
-                if (r < rows) {
-                    const float X = (float)x + u[r], Y = (float)(sy * SH + r) + v[r];
-                    const float fx0 = floorf(X), fy0 = floorf(Y);
-                    const bool ok = fx0 >= -1.f && fx0 < Wf && fy0 >= -1.f && fy0 < Hf;      // false for NaN / inf
-                    if (!ok) note_nonfinite(X, Y);
-                    if (ok) {
-                        const int x0 = (int)fx0, y0 = (int)fy0;
-                        bx0 = min(bx0, x0); bx1 = max(bx1, x0); by0 = min(by0, y0); by1 = max(by1, y0);
-                    }
-                }
-        }
-        bx0 = __reduce_min_sync(0xffffffffu, bx0); bx1 = __reduce_max_sync(0xffffffffu, bx1);
-        by0 = __reduce_min_sync(0xffffffffu, by0); by1 = __reduce_max_sync(0xffffffffu, by1);
-        if (lane == 0) fine[((long long)n * g.sty + sy) * g.stx + sx] = make_int4(bx0, bx1, by0, by1);
-        if (bx0 <= bx1) {
-            ux0 = min(ux0, bx0); ux1 = max(ux1, bx1); uy0 = min(uy0, by0); uy1 = max(uy1, by1);
-            // target tiles the box touches (corners reach one cell further right / down)
-            const int cx0 = max(bx0, 0) / TW, cx1 = min(bx1 + 1, g.W - 1) / TW;
-            const int cy0 = max(by0, 0) / g.th, cy1 = min(by1 + 1, g.H - 1) / g.th;
-            pairs += (cx1 - cx0 + 1) * (cy1 - cy0 + 1);
-            live += 1;
-        }
-    }
-    if (lane == 0) {
-        atomicMin(&s_box[0], ux0); atomicMax(&s_box[1], ux1); atomicMin(&s_box[2], uy0); atomicMax(&s_box[3], uy1);
-        atomicAdd(&s_amp[0], pairs); atomicAdd(&s_amp[1], live);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const long long si = ((long long)n * g.supy + blockIdx.y) * g.supx + blockIdx.x;
-        coarse[si] = make_int4(s_box[0], s_box[1], s_box[2], s_box[3]);
-        amp[si] = make_int2(s_amp[0], s_amp[1]);
-    }
-}
-
-__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-
-// walk of one source tile (8 rows x 32 lanes) by one warp, keeping the corners inside the target tile [Tx0, Tx1) x [Ty0, Ty1).
-// The warp stages the tile in its own 6 KB of shared memory with cp.async, in two dependent steps instead of one per row:
-// the flow of all eight rows first, then - for the rows some lane of which reaches the target tile - metric and channels.
-template <int WKIND, bool PRE>
-__device__ __forceinline__ void owner_walk(const View4& in, const View4& flow, const View4& metric, int n, int sx, int sy, int H, int W,
-                                           float4* scr, int Tx0, int Ty0, int Tx1, int Ty1, float* wbuf) {
-    using namespace own;
-    const int lane = threadIdx.x & 31, src_lane = (lane + 31) & 31;
-    const bool lane_gt0 = lane > 0;
-    const int x = sx * SW + lane;
-    const bool inb = x < W;
-    const int yb = sy * SH, rows = min(SH, H - yb);
-    const float xlo = (float)(Tx0 - 1), xhi = (float)(Tx1 - 1), ylo = (float)(Ty0 - 1), yhi = (float)(Ty1 - 1), ytop = (float)Ty0;
-    float* sb = wbuf + lane;                                     // [plane][row][32]: u, v, z, c0, c1, c2
-    __syncwarp();                                                // the previous walk of this warp has finished reading wbuf
-    if (inb) {
-        const float* fu = flow.p + n * flow.sn + (long long)yb * flow.sh + (long long)x * flow.sw;
-#pragma unroll
-        for (int r = 0; r < SH; ++r)
-            if (r < rows) {
-                cp_async4(sb + r * SW, fu + (long long)r * flow.sh);
-                cp_async4(sb + (SH + r) * SW, fu + flow.sc + (long long)r * flow.sh);
-            }
-    }
-    cp_async_wait_all();
-    // which rows reach the tile (warp-uniform mask)
-    const float xf = (float)x;
-    unsigned hit = 0;
-#pragma unroll
-    for (int r = 0; r < SH; ++r) {
-        bool pR = false;
-        if (r < rows && inb) {
-            const float fx0 = floorf(xf + sb[r * SW]), fy0 = floorf((float)(yb + r) + sb[(SH + r) * SW]);
-            pR = fx0 >= xlo && fx0 <= xhi && fy0 >= ylo && fy0 <= yhi;                   // false for NaN
-        }
-        if (__any_sync(0xffffffffu, pR)) hit |= 1u << r;
-    }
-    if (hit == 0) return;
-    if (inb) {
-        const float* zp = WKIND ? metric.p + n * metric.sn + (long long)yb * metric.sh + (long long)x * metric.sw : nullptr;
-        const float* ip = in.p + n * in.sn + (long long)yb * in.sh + (long long)x * in.sw;
-#pragma unroll
-        for (int r = 0; r < SH; ++r)
-            if (hit >> r & 1) {
-                if (WKIND) cp_async4(sb + (2 * SH + r) * SW, zp + (long long)r * metric.sh);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) cp_async4(sb + ((3 + j) * SH + r) * SW, ip + (long long)j * in.sc + (long long)r * in.sh);
-            }
-    }
-    cp_async_wait_all();
-    int prev_t = tile::kSent;
-    float pw[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-    for (int r = 0; r < rows; ++r) {
-        if (!(hit >> r & 1)) continue;                           // the row misses this tile
-        const float u = sb[r * SW], v = sb[(SH + r) * SW];
-        // softSplat.py:23-38
-        const float X = xf + u, Y = (float)(yb + r) + v;
-        const float fx0 = floorf(X), fy0 = floorf(Y);
-        const bool pR = inb && fx0 >= xlo && fx0 <= xhi && fy0 >= ylo && fy0 <= yhi;     // some corner may fall inside the tile (false for NaN)
-        float m = 1.f;
-        if (WKIND == 1) m = exp_splat(sb[(2 * SH + r) * SW]);
-        if (WKIND == 2) m = sb[(2 * SH + r) * SW];
-        float xv[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) xv[j] = sb[((3 + j) * SH + r) * SW];
-        const float x1f = fx0 + 1.f, y1f = fy0 + 1.f;
-        const bool pT = pR && fy0 >= ytop;                       // top corners inside the tile
-        const bool pB = pR && fy0 < yhi;                         // bottom corners inside the tile
-        const int cx = (int)x1f - Tx0;                           // scratch cell of the W corners (guard cell at 0)
-        const int y0 = (int)fy0 - Ty0;
-        const int tT = pT ? y0 * P + cx : tile::kSent;
-        const int tB = pB ? (y0 + 1) * P + cx : tile::kSent;
-        const float ax = x1f - X, bx = X - fx0, ay = y1f - Y, by = Y - fy0;
-        const float wNW = ax * ay, wNE = bx * ay, wSW = ax * by, wSE = bx * by;
-        const float hm = PRE ? 0.5f * m : m;                     // ((x+1)*0.5)*m == (x+1)*(0.5*m) exactly
-        float tW[4], tE[4], bW[4], bE[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float a;
-            if (j < 3) a = PRE ? (xv[j] + 1.f) * hm : xv[j] * m;
-            else a = m;
-            tW[j] = a * wNW; tE[j] = a * wNE; bW[j] = a * wSW; bE[j] = a * wSE;
-        }
-        // vertical: the bottom-W corner carried from the previous row joins this row's top-W corner, or is flushed
-        const bool vm = tT == prev_t;
-        red4_at(scr, vm ? tile::kSent : prev_t, pw);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tW[j] = vm ? tW[j] + pw[j] : tW[j];
-        // horizontal: the E corners travel to the lane on the right (rotate: lane 0 gets lane 31's and only forwards them)
-        const int rT = __shfl_sync(0xffffffffu, tT + 1, src_lane);
-        const int rB = __shfl_sync(0xffffffffu, tB + 1, src_lane);
-        float rt4[4], rb4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            rt4[j] = __shfl_sync(0xffffffffu, tE[j], src_lane);
-            rb4[j] = __shfl_sync(0xffffffffu, bE[j], src_lane);
-        }
-        const bool takeT = lane_gt0 && rT == tT, takeB = lane_gt0 && rB == tB;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            tW[j] = takeT ? tW[j] + rt4[j] : tW[j];
-            bW[j] = takeB ? bW[j] + rb4[j] : bW[j];
-        }
-        red4_at(scr, takeT ? tile::kSent : rT, rt4);
-        red4_at(scr, takeB ? tile::kSent : rB, rb4);
-        red4_at(scr, tT, tW);
-        prev_t = tB;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pw[j] = bW[j];
-    }
-    red4_at(scr, prev_t, pw);
-}
-
-// verdict: 0 = smooth (the owner kernel produced the output), 1 = rough (the three-pass kernels must run)
-template <int WKIND, bool PRE>
-__global__ void __launch_bounds__(own::NT, 2) splat_owner_kernel(View4 in, View4 flow, View4 metric, float* __restrict__ out,
-                                                                 float* __restrict__ norm_out, const int4* __restrict__ fine,
-                                                                 const int4* __restrict__ coarse, const int2* __restrict__ amp,
-                                                                 float4* __restrict__ scratch, int* __restrict__ verdict, own::Geom g,
-                                                                 int max_pairs_x4, int mode_raw) {
-    using namespace own;
-    __shared__ int s_list[LIST];
-    __shared__ int s_sup[NT];
-    __shared__ int s_n, s_nsup, s_next, s_sum[2];
-    extern __shared__ __align__(16) float s_stage[];          // [warps][6 planes][8 rows][32]: each warp's staging buffer
-    const int tid = threadIdx.x, lane = tid & 31;
-    float* wbuf = s_stage + (tid >> 5) * (6 * SH * SW);
-    const int nsup = g.supx * g.supy;
-    // ---- verdict from the pre-pass' pair counts: examined (source tile, target tile) pairs per live source tile
-    if (tid == 0) { s_sum[0] = 0; s_sum[1] = 0; }
-    __syncthreads();
-    {
-        int a = 0, b = 0;
-        for (int i = tid; i < g.N * nsup; i += NT) { const int2 t = __ldg(amp + i); a += t.x; b += t.y; }
-        a = __reduce_add_sync(0xffffffffu, a); b = __reduce_add_sync(0xffffffffu, b);
-        if (lane == 0) { atomicAdd(&s_sum[0], a); atomicAdd(&s_sum[1], b); }
-    }
-    __syncthreads();
-    const bool rough = (long long)s_sum[0] * 4 > (long long)s_sum[1] * max_pairs_x4;
-    if (blockIdx.x == 0 && tid == 0) *verdict = rough ? 1 : 0;
-    if (rough) return;
-    const int scr_cells = g.th * P;
-    float4* scr = scratch + (size_t)blockIdx.x * scr_cells;
-    for (int i = tid; i < scr_cells; i += NT) scr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    const int tiles_per_frame = g.ttx * g.tty, ntiles = g.N * tiles_per_frame;
-    const long long HW = (long long)g.H * g.W;
-    for (int tidx = blockIdx.x; tidx < ntiles; tidx += gridDim.x) {
-        const int n = tidx / tiles_per_frame, trem = tidx - n * tiles_per_frame;
-        const int ty = trem / g.ttx, tx = trem - ty * g.ttx;
-        const int Tx0 = tx * TW, Ty0 = ty * g.th, Tx1 = min(Tx0 + TW, g.W), Ty1 = min(Ty0 + g.th, g.H);
-        // a box touches the tile iff its NW corners reach [Tx0 - 1, Tx1 - 1] x [Ty0 - 1, Ty1 - 1]
-        auto touches = [&](const int4& b) { return b.y >= Tx0 - 1 && b.x <= Tx1 - 1 && b.w >= Ty0 - 1 && b.z <= Ty1 - 1; };
-        auto process_list = [&]() {                       // all warps: source tiles of s_list, handed out dynamically
-            __syncthreads();
-            const int cnt = s_n;
-            for (;;) {
-                int k = 0;
-                if (lane == 0) k = atomicAdd(&s_next, 1);
-                k = __shfl_sync(0xffffffffu, k, 0);
-                if (k >= cnt) break;
-                const int st = s_list[k];
-                owner_walk<WKIND, PRE>(in, flow, metric, n, st % g.stx, st / g.stx, g.H, g.W, scr, Tx0, Ty0, Tx1, Ty1, wbuf);
-            }
-            __syncthreads();
-            if (tid == 0) { s_n = 0; s_next = 0; }
-            __syncthreads();
-        };
-        if (tid == 0) { s_n = 0; s_next = 0; }
-        for (int c0 = 0; c0 < nsup; c0 += NT) {
-            if (tid == 0) s_nsup = 0;
-            __syncthreads();
-            if (c0 + tid < nsup && touches(__ldg(coarse + (long long)n * nsup + c0 + tid))) s_sup[atomicAdd(&s_nsup, 1)] = c0 + tid;
-            __syncthreads();
-            const int ns = s_nsup;
-            for (int g0 = 0; g0 < ns; g0 += NT / (SUP * SUP)) {
-                const int gi = g0 + tid / (SUP * SUP);
-                if (gi < ns) {
-                    const int su = s_sup[gi], f = tid % (SUP * SUP);
-                    const int sx = (su % g.supx) * SUP + (f % SUP), sy = (su / g.supx) * SUP + (f / SUP);
-                    if (sx < g.stx && sy < g.sty && touches(__ldg(fine + ((long long)n * g.sty + sy) * g.stx + sx)))
-                        s_list[atomicAdd(&s_n, 1)] = sy * g.stx + sx;
-                }
-                if (__syncthreads_or(s_n > LIST - NT)) process_list();      // uniform verdict: the last thread to append sees the final count
-            }
-        }
-        process_list();
-        // ---- all reductions of this tile are performed: normalise, store, re-zero (softSplat.py:343-349)
-        __threadfence();
-        __syncthreads();
-        const int rows = Ty1 - Ty0;
-        for (int i = tid; i < g.th * (TW / 4); i += NT) {
-            const int r = i >> 5, g4 = i & 31;
-            float4* cp = scr + r * P + 1 + 4 * g4;
-            float4 c[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) c[k] = __ldcg(cp + k);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) cp[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g4 == 0) cp[-1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g4 == 31) cp[4] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int x = Tx0 + 4 * g4, y = Ty0 + r;
-            if (r < rows && x < g.W) {
-                float d[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) d[k] = norm_recip(c[k].w);
-                const long long pix = (long long)y * g.W + x;
-                float* op = out + (long long)n * 3 * HW + pix;
-                const float o0[4] = {post_scale(c[0].x, d[0], mode_raw, true), post_scale(c[1].x, d[1], mode_raw, true), post_scale(c[2].x, d[2], mode_raw, true), post_scale(c[3].x, d[3], mode_raw, true)};
-                const float o1[4] = {post_scale(c[0].y, d[0], mode_raw, true), post_scale(c[1].y, d[1], mode_raw, true), post_scale(c[2].y, d[2], mode_raw, true), post_scale(c[3].y, d[3], mode_raw, true)};
-                const float o2[4] = {post_scale(c[0].z, d[0], mode_raw, true), post_scale(c[1].z, d[1], mode_raw, true), post_scale(c[2].z, d[2], mode_raw, true), post_scale(c[3].z, d[3], mode_raw, true)};
-                vstore<4>(op, o0); vstore<4>(op + HW, o1); vstore<4>(op + 2 * HW, o2);
-                if (norm_out) { const float nn[4] = {c[0].w, c[1].w, c[2].w, c[3].w}; vstore<4>(norm_out + (long long)n * HW + pix, nn); }
-            }
-        }
-        __threadfence();                                 // the zeros are in L2 before the next tile's reductions arrive there
-        __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Pass 2: normalise + post-scale + quad-interleaved -> NCHW.  One thread per (PX consecutive pixels, channel quad):
 // PX float4 loads of the accumulator (+ PX of the quad holding the normaliser), 4 channel-plane stores of PX floats.
 //   softSplat.py:343-349: norm==0 -> 1, divide, (y - 0.5) * 2 (post-scale in every mode but RAW).
@@ -1140,12 +821,6 @@ static int plan_fwd(int mode, int N, int C, int H, int W, bool has_metric, FwdPl
     p.Q = p.g.CP / 4;
     if ((long long)H * (W + 2) >= (1ll << 30)) return FLDR_ERR_UNSUPPORTED;       // 32-bit cell offsets inside a plane
     p.acc_bytes = align_up((size_t)N * p.Q * H * (W + 2) * 16, 256);
-    {   // tile-owner path: bounding boxes of the source tiles / super-tiles, pair counts, verdict word
-        const size_t stx = (W + own::SW - 1) / own::SW, sty = (H + own::SH - 1) / own::SH;
-        const size_t supx = (stx + own::SUP - 1) / own::SUP, supy = (sty + own::SUP - 1) / own::SUP;
-        p.acc_bytes += align_up((size_t)N * sty * stx * 16, 256) + align_up((size_t)N * supy * supx * 16, 256) +
-                       align_up((size_t)N * supy * supx * 8, 256) + 256;
-    }
     return FLDR_OK;
 }
 
@@ -1232,51 +907,6 @@ static int launch_forward(const FwdPlan& p, const View4& vin, const View4& vfl, 
         cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(256), args, 0, s);
         if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
         return FLDR_OK;
-    }
-    // tile-owner path: big image splats (C = 3 + normaliser) with unit pixel stride
-    if (get_option(kOptSplatOwner) != 0 && Q == 1 && g.C == 3 && g.CA == 4 && (size_t)n4 * 16 > (48u << 20) && (W % 4) == 0 &&
-        vin.sw == 1 && vfl.sw == 1 && (!g.has_metric || vme.sw == 1) && aligned16(out) && (!norm || aligned16(norm))) {
-        own::Geom og;
-        og.N = N; og.H = H; og.W = W;
-        og.stx = (W + own::SW - 1) / own::SW; og.sty = (H + own::SH - 1) / own::SH;
-        og.supx = (og.stx + own::SUP - 1) / own::SUP; og.supy = (og.sty + own::SUP - 1) / own::SUP;
-        const int grid = 2 * sm_count();
-        og.ttx = (W + own::TW - 1) / own::TW;
-        // target tile height: the one that minimises (rounds of tiles over the persistent grid) x (rows per tile)
-        int best_th = 32;
-        long long best_cost = -1;
-        for (int th = 32; th <= 48; th += 4) {
-            const long long tiles = (long long)N * og.ttx * ((H + th - 1) / th);
-            const long long cost = ((tiles + grid - 1) / grid) * th;
-            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_th = th; }
-        }
-        og.th = best_th;
-        og.tty = (H + og.th - 1) / og.th;
-        // workspace: [accumulator / scratch][fine boxes][coarse boxes][pair counts][verdict]
-        char* wsb = reinterpret_cast<char*>(acc);
-        size_t off = align_up((size_t)N * Q * H * (W + 2) * 16, 256);
-        int4* fine = reinterpret_cast<int4*>(wsb + off); off += align_up((size_t)N * og.sty * og.stx * 16, 256);
-        int4* coarse = reinterpret_cast<int4*>(wsb + off); off += align_up((size_t)N * og.supy * og.supx * 16, 256);
-        int2* amp = reinterpret_cast<int2*>(wsb + off); off += align_up((size_t)N * og.supy * og.supx * 8, 256);
-        int* verdict = reinterpret_cast<int*>(wsb + off);
-        if ((size_t)grid * og.th * own::P * 16 <= (size_t)N * Q * H * (W + 2) * 16 && (long long)N * og.supy <= 65535 * 1ll && N <= 65535) {
-            splat_bbox_kernel<<<dim3(og.supx, og.supy, N), own::NT, 0, s>>>(vfl, fine, coarse, amp, og);
-            const int max_pairs_x4 = get_option(kOptSplatOwnerPairs);      // examined pairs per live source tile, x 4
-            const size_t stage_bytes = (size_t)(own::NT / 32) * 6 * own::SH * own::SW * 4;      // 96 KB: two CTAs per SM
-#define FLDR_LAUNCH_OWNER(WK_, PRE_)                                                                                                      \
-    do {                                                                                                                                  \
-        cudaFuncSetAttribute(splat_owner_kernel<WK_, PRE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);               \
-        splat_owner_kernel<WK_, PRE_><<<grid, own::NT, stage_bytes, s>>>(vin, vfl, vme, out, norm, fine, coarse, amp,                     \
-                                                                         reinterpret_cast<float4*>(acc), verdict, og, max_pairs_x4, 0);   \
-    } while (0)
-            if (wkind == 1) FLDR_LAUNCH_OWNER(1, true);
-            else if (wkind == 2) FLDR_LAUNCH_OWNER(2, false);
-            else if (pre) FLDR_LAUNCH_OWNER(0, true);
-            else FLDR_LAUNCH_OWNER(0, false);
-#undef FLDR_LAUNCH_OWNER
-            if ((st = check_launch()) != FLDR_OK) return st;
-            if (get_option(kOptSplatOwner) == 2) return FLDR_OK;            // EXPERIMENT: no fallback launches
-        }
     }
     {
         cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)N * Q * H * (W + 2) * 16, s);
