@@ -45,6 +45,12 @@ def synthetic_triplet(H=2160, W=4096, seed=0):
 
 
 def worker(impl, out_path, reps, height, width):
+    # This worker is its own process and runs the reference checkout as it is (its checkpoint is a pickle: torch.load with
+    # weights_only=False below) - that trust in /root/reference's files is inherent to an end-to-end run of the reference.
+    try:        # bench.py pins its rank to the cores next to its GPU for the PCIe legs; this leg's host work (the reference builds
+        os.sched_setaffinity(0, range(os.cpu_count()))      # mesh grids on the CPU in every bwarp call) gets every core back
+    except (AttributeError, OSError):
+        pass
     import torch
     if impl.startswith("ours"):
         sys.path.insert(0, os.path.join(ROOT, "fldr-vfi_b200", "dropin"))

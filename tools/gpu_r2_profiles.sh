@@ -13,4 +13,5 @@ timeout 300 python tools/train_probe.py > gpurun_out/r2_train_probe.txt 2>&1
 timeout 300 python tools/overhead_probe.py > gpurun_out/r2_host_overhead.txt 2>&1
 FLDR_B200_NO_EXT=1 timeout 300 python tools/overhead_probe.py > gpurun_out/r2_host_overhead_ctypes.txt 2>&1
 timeout 300 python tools/splat_probe.py > gpurun_out/r2_splat_probe.txt 2>&1
+timeout 300 python tools/bwd_probe.py > gpurun_out/r2_bwd_probe.txt 2>&1
 tail -c 300 gpurun_out/r2_bench_full.json; echo; cat gpurun_out/r2_train_probe.txt
