@@ -707,6 +707,44 @@ def next_rows_probe(devin, peak):
             out["pca_features_6xHxW_f32out"]["reference_text_same_gpu_ms"] = round(ms_ref, 4)
     except Exception as exc:      # a reported baseline must never take the bench down
         out["pca_features_6xHxW_f32out"]["reference_text_same_gpu_ms"] = f"unavailable: {type(exc).__name__}"
+    # rank 4, second half: the input pyramid (main.py:855-856) - five bicubic levels of the two padded frames in one launch
+    import fldr_vfi_b200.pyramid as Py
+    import torch.nn.functional as F
+    frames5 = torch.stack([x0, x1], 2).contiguous()                   # [N, C, T=2, H, W]
+    scales = [8, 16, 32, 64, 128, 256]
+    def med_dev(fn, reps=4):     # calls shorter than their host-side launch cost: let the host run ahead behind a spin kernel
+        fn()
+        ts = []
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(400000)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / reps)
+        return sorted(ts)[len(ts) // 2]
+
+    with torch.no_grad():
+        ms = med_dev(lambda: Py.input_pyramid(frames5, scales, 5))
+    nbytes = int(4 * N * C * 2 * sum((H >> k) * (W >> k) for k in range(6)))
+    out["input_pyramid_5_levels"] = {"ms_per_call": round(ms, 4), "algorithmic_bytes": nbytes, "GBps": round(nbytes / ms / 1e6, 1),
+                                     "frac_of_peak": round(nbytes / ms / 1e6 / peak, 3)}
+    try:
+        planes = frames5.permute(0, 2, 1, 3, 4).reshape(N * 2, C, H, W)
+        with torch.no_grad():       # torch's own CUDA bicubic, one call per level (what moving the reference's expression to the GPU gives)
+            out["input_pyramid_5_levels"]["torch_cuda_interpolate_ms"] = round(
+                med_dev(lambda: [F.interpolate(planes, scale_factor=1.0 / (1 << k), mode="bicubic", align_corners=False) for k in range(1, 6)]), 4)
+        host = planes.cpu()
+        t0 = time.perf_counter()   # the reference as written: CPU bicubic per level + a pageable H2D copy per level (one repetition)
+        with torch.no_grad():
+            lv = [F.interpolate(host, scale_factor=1.0 / (1 << k), mode="bicubic", align_corners=False).to(x0.device) for k in range(1, 6)]
+        torch.cuda.synchronize()
+        out["input_pyramid_5_levels"]["reference_expression_cpu_plus_h2d_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
+        del lv
+    except Exception as exc:
+        out["input_pyramid_5_levels"]["torch_cuda_interpolate_ms"] = f"unavailable: {type(exc).__name__}"
     return out
 
 

@@ -55,6 +55,9 @@ SYMBOLS = {
     "fldr_pca_features_fwd": (ctypes.c_int, [c_float_p, c_i64_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "fldr_bicubic_pyramid_fwd": (ctypes.c_int, [c_float_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_int,
+                                                ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
 }
 
 SPLAT_MODES = {"summation": 0, "average": 1, "linear": 2, "softmax": 3, "raw": 4}

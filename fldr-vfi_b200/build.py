@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfldr_b200.so")
 STAMP = os.path.join(HERE, ".libfldr_b200.stamp")
-SOURCES = ["cabi.cu", "splat.cu", "corr.cu", "warp.cu", "blend.cu", "pca.cu"]
+SOURCES = ["cabi.cu", "splat.cu", "corr.cu", "warp.cu", "blend.cu", "pca.cu", "pyramid.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-Xlinker", "-soname=libfldr_b200.so", "--use_fast_math=false"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]  # precise math: parity bar is 1e-5 relative

@@ -241,6 +241,25 @@ int fldr_pca_features_fwd(const float* im, const int64_t* im_strides, const doub
                           int64_t ev_row_stride, const double* mean_vec, void* out, int out_is_f32,
                           int chan, int H, int W, int ncomp, void* ws, size_t ws_bytes, fldr_stream_t stream);
 
+/* ------------------------------------- input pyramid (next row, SURVEY 8f-4, second half) --------------------------- */
+
+/*
+ * main.py:855-856 (test) / 562-563 (train): level i > 0 of `input_gpu` is
+ *   F.interpolate(frames, scale_factor = scales[0] / scales[i], mode = 'bicubic', align_corners = args.align_cornerse)
+ * of the full-resolution (padded) frames, computed by the reference on the CPU and copied to the device level by level.
+ * Here the frames are on the device and every level is written by one call (one launch for the shipped presets: factors
+ * 1/2, 1/4, ... 1/32 with align_corners = 0; any other factor list / align_corners = 1 takes one generic launch per level).
+ * Arithmetic follows ATen's upsample_bicubic2d (A = -0.75, taps clamped to the frame, horizontal sums first).
+ *   frames         [planes, H, W] float32 (planes = B * C * T: interpolation is per plane), unit pixel stride,
+ *                  row_stride / plane_stride in elements
+ *   scale_factors  host array of n_levels doubles (scales[0] / scales[i]); level i has floor(H * f_i) x floor(W * f_i) pixels
+ *   out_levels     host array of n_levels device pointers, level i contiguous [planes, floor(H f_i), floor(W f_i)] float32
+ * No workspace.  Empty pyramids (n_levels = 0) and zero planes succeed without a launch.
+ */
+int fldr_bicubic_pyramid_fwd(const float* frames, int64_t plane_stride, int64_t row_stride, int planes, int H, int W,
+                             int n_levels, const double* scale_factors, int align_corners, float* const* out_levels,
+                             fldr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -183,7 +183,41 @@ def pca_case(name, chan, H, W, seed, mean_vector_norm):
     print(name, tuple(out.shape), out.dtype, float(out.min()), float(out.max()))
 
 
+def pyramid_case(name, B, T, H, W, scales, n_levels, seed, align_corners=False, noise=False):
+    """main.py's own list comprehension building ``input_gpu`` in ``test()`` (855-856), lifted by ast and evaluated on the
+    CPU (``device = 'cpu'``) - ``F.interpolate(..., mode='bicubic')`` of the full-resolution frames per level."""
+    import ast
+    import types
+    import torch.nn.functional as F
+    src = open("/root/reference/main.py").read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "test")
+    stmt = next(n for n in ast.walk(fn) if isinstance(n, ast.Assign) and isinstance(n.targets[0], ast.Name)
+                and n.targets[0].id == "input_gpu" and isinstance(n.value, ast.ListComp))
+    code = textwrap.dedent(ast.get_source_segment(src, stmt))
+    C = 3
+    if noise:
+        frames = torch.randn(B, C, T, H, W, generator=torch.Generator().manual_seed(seed))     # white noise: every tap matters
+    else:
+        frames = synth.image(B, C * T, H, W, seed=seed).reshape(B, C, T, H, W).contiguous()
+    args = types.SimpleNamespace(scales=list(scales), S_tst=n_levels, align_cornerse=align_corners)
+    ns = {"torch": torch, "F": F, "args": args, "device": "cpu", "input_frames": frames, "B": B, "C": C, "T": T, "H": H, "W": W}
+    with torch.no_grad():
+        exec(compile(code, "main.py:855-856", "exec"), ns)
+    levels = ns["input_gpu"]
+    assert len(levels) == n_levels + 1 and levels[0].shape == frames.shape
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), frames=frames.numpy(), scales=np.array(scales, dtype=np.int64),
+                        n_levels=np.int32(n_levels), align_corners=np.int32(align_corners),
+                        **{f"level{i}": levels[i].contiguous().numpy() for i in range(1, n_levels + 1)})
+    print(name, [tuple(l.shape) for l in levels])
+
+
 if __name__ == "__main__":
+    if "--pyramid-only" in sys.argv:
+        pyramid_case("pyramid_5lv", 1, 2, 64, 256, [8, 16, 32, 64, 128, 256], 5, 510)            # --test5scales: factors 1/2 .. 1/32
+        pyramid_case("pyramid_noise_b2", 2, 2, 32, 160, [8, 16, 32, 64], 3, 520, noise=True)     # B = 2, W not a multiple of 128
+        pyramid_case("pyramid_ac", 1, 2, 24, 40, [8, 16, 32], 2, 530, align_corners=True)        # --align_cornerse
+        pyramid_case("pyramid_odd", 1, 2, 20, 36, [8, 24, 40], 2, 540, noise=True)               # factors 1/3, 1/5: generic taps
+        sys.exit(0)
     if "--pca-only" in sys.argv:
         pca_case("pca_6x32x48", 6, 32, 48, 410, True)          # one sample (two RGB frames), mean-vector normalisation on
         pca_case("pca_12x16x24_nomv", 12, 16, 24, 420, False)  # B = 2, no mean-vector normalisation

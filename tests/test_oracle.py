@@ -261,3 +261,38 @@ def test_pca_rejects_unpadded_frames():
     from oracle import pca_oracle
     with pytest.raises(Exception):
         pca_oracle.to_pca_diff(torch.zeros(6, 12, 16), torch.zeros(64, dtype=torch.float64), torch.zeros(16, 64, dtype=torch.float64))
+
+
+PYRAMID_CASES = ["pyramid_5lv", "pyramid_noise_b2", "pyramid_ac", "pyramid_odd"]
+PYRAMID_TOL = 2e-6       # float32, 16 taps: x max|frame| - fma contraction / vector order of ATen's kernel vs the plain restatement
+
+
+@pytest.mark.parametrize("name", PYRAMID_CASES)
+def test_pyramid_restatement_vs_reference_expression(name):
+    """oracle/pyramid_oracle.py against the reference's own list comprehension (main.py:855-856) evaluated on the CPU."""
+    import numpy as np
+    from oracle import pyramid_oracle as po
+    g = load_golden(name)
+    frames = g["frames"].numpy()
+    n = int(g["n_levels"])
+    levels = po.input_pyramid(frames, [int(s) for s in g["scales"]], n, bool(int(g["align_corners"])))
+    assert len(levels) == n + 1 and levels[0].shape == frames.shape
+    for i in range(1, n + 1):
+        ref = g[f"level{i}"].numpy()
+        assert levels[i].shape == ref.shape and levels[i].dtype == np.float32
+        assert float(np.abs(levels[i] - ref).max()) <= PYRAMID_TOL * max(1.0, float(np.abs(frames).max()))
+
+
+def test_pyramid_kat_constant_and_half_pixel_weights():
+    """Known answers: a constant frame stays constant on every level (the cubic weights sum to 1), and for the factors
+    1/2^k every output uses the weights (-3/32, 19/32, 19/32, -3/32) at rows / columns 2^k d + 2^(k-1) - 2 .. + 1."""
+    import numpy as np
+    from oracle import pyramid_oracle as po
+    const = np.full((1, 16, 32), 0.37, dtype=np.float32)
+    for f in (0.5, 0.25, 1 / 3):
+        assert float(np.abs(po.bicubic_resize(const, f) - np.float32(0.37)).max()) <= 1e-7
+    for k in (1, 2, 3):
+        taps, w = po.axis_taps(64, 64 >> k, 1.0 / (1 << k), False)
+        assert np.array_equal(w, np.tile(np.float32([-0.09375, 0.59375, 0.59375, -0.09375]), (64 >> k, 1)))
+        d = np.arange(64 >> k)[:, None]
+        assert np.array_equal(taps, np.clip((d << k) + (1 << (k - 1)) - 2 + np.arange(4)[None, :], 0, 63))
