@@ -34,7 +34,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int sm_count();
 
 // tuning / diagnostic options (fldr_set_option); defaults may come from FLDR_<NAME> environment variables
-enum Option { kOptSplatStream = 0, kOptSplatFusedMax = 1, kOptCorrTh = 2, kOptSplatPfRows = 3, kOptCorrBwdRows = 4, kOptCount = 5 };
+enum Option { kOptSplatStream = 0, kOptSplatFusedMax = 1, kOptCorrTh = 2, kOptSplatPfRows = 3, kOptCorrBwdRows = 4, kOptSplatSnake = 5, kOptCount = 6 };
 int get_option(int opt);
 
 // red.global.add.v4.f32 (sm_90+): one 16-byte reduction request instead of four scalar REDs.

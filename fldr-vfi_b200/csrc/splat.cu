@@ -296,12 +296,14 @@ __global__ void __launch_bounds__(tile::TW, 6) splat_scatter_tile_kernel(const _
                                                                          const __grid_constant__ CUtensorMap tm_flow,
                                                                          const __grid_constant__ CUtensorMap tm_metric,
                                                                          float* __restrict__ acc, SplatGeom g, int Q, int nbox,
-                                                                         int pf_rows) {
+                                                                         int pf_rows, int flip) {
     using namespace tile;
     __shared__ __align__(128) float st[PLANES * R * TW];
     __shared__ uint64_t bar;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int x0 = blockIdx.x * TW, yb = blockIdx.y * R;
+    // flip: tiles are dispatched bottom-up, so the scatter starts on the accumulator rows the zero fill wrote LAST (still in L2)
+    // and ends on the rows the normalise pass reads FIRST
+    const int x0 = blockIdx.x * TW, yb = (flip ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y) * R;
     const int q = blockIdx.z % Q, n = blockIdx.z / Q;
     const int nch = QS == 1 ? 3 : QS == 2 ? 4 : min(4, g.C - q * 4);
     const int wslot = QS == 1 ? 3 : QS == 2 ? -1 : ((g.CA > g.C) ? g.C - q * 4 : -1);
@@ -393,6 +395,17 @@ __global__ void __launch_bounds__(tile::TW, 6) splat_scatter_tile_kernel(const _
         for (int j = 0; j < 4; ++j) pw[j] = bW[j];
     }
     red4_at(rq, prev_t, pw);
+}
+
+// Zero fill with ordinary (L2-allocating) stores, front to back: what it wrote last is what the bottom-up scatter touches first.
+__global__ void __launch_bounds__(256) splat_zero_kernel(float4* __restrict__ acc, long long n4) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long i0 = (long long)blockIdx.x * (256 * 8) + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const long long i = i0 + k * 256;
+        if (i < n4) acc[i] = z;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -908,7 +921,12 @@ static int launch_forward(const FwdPlan& p, const View4& vin, const View4& vfl, 
         if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
         return FLDR_OK;
     }
-    {
+    const int snake = get_option(kOptSplatSnake) != 0 && N * Q == 1;
+    if (snake) {
+        const long long cells = (long long)N * Q * H * (W + 2);
+        splat_zero_kernel<<<(unsigned)((cells + 2047) / 2048), 256, 0, s>>>(reinterpret_cast<float4*>(acc), cells);
+        if ((st = check_launch()) != FLDR_OK) return st;
+    } else {
         cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)N * Q * H * (W + 2) * 16, s);
         if (e != cudaSuccess) { set_last_cuda_error(e); return FLDR_ERR_CUDA; }
     }
@@ -928,7 +946,7 @@ static int launch_forward(const FwdPlan& p, const View4& vin, const View4& vfl, 
     if (tiled) {
         dim3 grid((W + tile::TW - 1) / tile::TW, (H + tile::R - 1) / tile::R, N * Q);
 #define FLDR_LAUNCH_TILE2(WK_, PRE_, QS_) \
-    splat_scatter_tile_kernel<WK_, PRE_, QS_><<<grid, tile::TW, 0, s>>>(tm_in, tm_fl, tm_me, acc, g, Q, nbox, pf)
+    splat_scatter_tile_kernel<WK_, PRE_, QS_><<<grid, tile::TW, 0, s>>>(tm_in, tm_fl, tm_me, acc, g, Q, nbox, pf, snake)
 #define FLDR_LAUNCH_TILE(WK_, PRE_)                                       \
     do {                                                                  \
         if (qs == 1) FLDR_LAUNCH_TILE2(WK_, PRE_, 1);                     \
