@@ -29,7 +29,7 @@ int sm_count() {
 namespace fldr {
 static const char* const kOptionNames[kOptCount] = {"splat_tma", "splat_fused_max", "corr_th", "splat_pf_rows", "corr_bwd_rows", "splat_snake"};
 static const char* const kOptionEnv[kOptCount] = {"FLDR_SPLAT_TMA", "FLDR_SPLAT_FUSED_MAX", "FLDR_CORR_TH", "FLDR_SPLAT_PF_ROWS", "FLDR_CORR_BWD_ROWS", "FLDR_SPLAT_SNAKE"};
-static const int kOptionDefault[kOptCount] = {1, 40000, 0, 0, 1, 0};
+static const int kOptionDefault[kOptCount] = {1, 40000, 0, 0, 1, 1};
 static int g_options[kOptCount];
 static std::once_flag g_options_once;
 static void init_options() {

@@ -74,6 +74,9 @@ int fldr_last_cuda_error(void);
  *   "splat_pf_rows"  accumulator rows prefetched into L2 ahead of the scatter (0 = default 4, negative = off)
  *   "corr_bwd_rows"  1 (default): correlation backward with three output rows per thread and gradOut streamed through a TMA
  *                    ring when the views allow it and C <= 32; 2 = for every C; 0 = always the 4-row tile kernel
+ *   "splat_snake"    1 (default): the three passes of the whole-frame splat run in alternating row order (zero fill front to back
+ *                    with L2-allocating stores, scatter back to front, normalise front to back) so that each starts on the
+ *                    accumulator lines its predecessor left in L2; 0 = cudaMemsetAsync + every pass front to back
  * Results are identical (within the summation-order tolerance) for every setting.
  */
 int fldr_set_option(const char* name, int value);
