@@ -551,6 +551,18 @@ def flow_regimes_probe(splat, devin, peak):
             ms, lo, hi = median_event_ms(lambda: splat(t["x"], fl, t["z"]))
             out[reg] = {"ms_per_call": round(ms, 4), "min_ms": round(lo, 4), "max_ms": round(hi, 4),
                         "GBps": round(nbytes / ms / 1e6, 1), "frac_of_peak": round(nbytes / ms / 1e6 / peak, 3)}
+        # two more points on the same axis (not SURVEY regimes): zero flow, and F1's amplitude (sigma 16 px) on a control grid 8x
+        # coarser (local stretch ~4 % instead of ~35 %: closer to real inter-frame motion).  The scatter pass is bound by the
+        # number of 32-byte sectors its reductions touch, which is what the flow's local stretch sets.
+        import torch.nn.functional as F
+        g = torch.Generator().manual_seed(61)
+        lo_res = torch.randn(N, 2, max(H // 512, 2), max(W // 512, 2), generator=g) * (16.0 * W / 4096.0)
+        extra = {"F0_zero": torch.zeros(N, 2, H, W), "F1_gentle_stretch": F.interpolate(lo_res, size=(H, W), mode="bilinear", align_corners=False).contiguous()}
+        for reg, fl_host in extra.items():
+            fl = fl_host.to(t["x"].device)
+            ms, lo, hi = median_event_ms(lambda: splat(t["x"], fl, t["z"]))
+            out[reg] = {"ms_per_call": round(ms, 4), "min_ms": round(lo, 4), "max_ms": round(hi, 4),
+                        "GBps": round(nbytes / ms / 1e6, 1), "frac_of_peak": round(nbytes / ms / 1e6 / peak, 3)}
     return out
 
 
