@@ -228,13 +228,13 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # our kernels launched per step (driver memsets not counted): splat = scatter + normalise, or ONE cooperative kernel
-    # for frames with <= 40000 accumulator float4s (fldr_set_option "splat_fused_max"); correlation = 1
+    # our kernels launched per step (driver memsets not counted): splat = zero fill + scatter + normalise, or ONE cooperative
+    # kernel for frames with <= 40000 accumulator float4s (fldr_set_option "splat_fused_max"); correlation = 1
     def kernels_of(n, t):
         if not n.startswith("splat"):
             return 1
         N, C, H, W = t["x"].shape
-        return 1 if N * ((C + 1 + 3) // 4) * H * W <= 40000 else 2
+        return 1 if N * ((C + 1 + 3) // 4) * H * W <= 40000 else 3
     launches_per_step = sum(kernels_of(n, t) for n, t in host)
 
     with torch.no_grad():

@@ -948,7 +948,9 @@ static int launch_forward(const FwdPlan& p, const View4& vin, const View4& vfl, 
     const int qs = (g.C == 3 && g.CA == 4) ? 1 : (g.CA == g.C && g.C % 4 == 0) ? 2 : 0;
     // accumulators larger than ~half the L2 are DRAM-resident when the reductions arrive: prefetch their lines
     const int pf_opt = get_option(kOptSplatPfRows);
-    const int pf = ((size_t)n4 * 16 > (48u << 20)) ? (pf_opt > 0 ? pf_opt : (pf_opt < 0 ? 0 : 4)) : 0;
+    // (with the alternating row order the scatter starts on lines the zero fill left in L2 and the prefetch no longer pays: 175.6
+    //  -> 173.6 us without it; it stays the default for the front-to-back order, where it was worth 133 -> 115 us)
+    const int pf = ((size_t)n4 * 16 > (48u << 20)) ? (pf_opt > 0 ? pf_opt : (pf_opt < 0 || snake ? 0 : 4)) : 0;
     bool tiled = get_option(kOptSplatStream) != 0 && view_tma_ok(vin) && view_tma_ok(vfl) && (!g.has_metric || (view_tma_ok(vme) && g.C < 4));
     CUtensorMap tm_in, tm_fl, tm_me;
     const int nbox = (Q == 1) ? g.C : 4;               // channels per input box

@@ -71,7 +71,8 @@ int fldr_last_cuda_error(void);
  *   "splat_fused_max" frames with at most this many accumulator float4s (N * ceil((C+1)/4) * H * W, default 40000)
  *                    run zero + scatter + normalise as ONE cooperative launch; 0 disables
  *   "corr_th"        tile height of the correlation forward kernel: 0 automatic, 8 or 16 forced
- *   "splat_pf_rows"  accumulator rows prefetched into L2 ahead of the scatter (0 = default 4, negative = off)
+ *   "splat_pf_rows"  accumulator rows prefetched into L2 ahead of the scatter (0 = default: 4 with splat_snake 0, none with
+ *                    splat_snake 1; negative = off)
  *   "corr_bwd_rows"  1 (default): correlation backward with three output rows per thread and gradOut streamed through a TMA
  *                    ring when the views allow it and C <= 32; 2 = for every C; 0 = always the 4-row tile kernel
  *   "splat_snake"    1 (default): the three passes of the whole-frame splat run in alternating row order (zero fill front to back
