@@ -46,7 +46,7 @@ def test_status_strings_and_version(lib):
 
 def test_options_roundtrip(lib):
     """fldr_set_option / fldr_get_option: every documented switch exists, unknown names are rejected."""
-    for name in (b"splat_tma", b"splat_fused_max", b"corr_th", b"splat_pf_rows"):
+    for name in (b"splat_tma", b"splat_fused_max", b"corr_th", b"splat_pf_rows", b"corr_bwd_rows", b"splat_snake"):
         old = lib.fldr_get_option(name)
         assert lib.fldr_set_option(name, 7) == 0 and lib.fldr_get_option(name) == 7
         assert lib.fldr_set_option(name, old) == 0
@@ -66,7 +66,7 @@ def test_workspace_sizes(lib):
     assert lib.fldr_splat_fwd_workspace_bytes(9, 1, 3, 8, 8) == 0          # unknown mode
     # the size depends on the shape only: tuning options must not change it (a size cached per shape stays valid)
     ws0 = lib.fldr_splat_fwd_workspace_bytes(3, 1, 3, 2304, 4096)
-    for name, val in ((b"splat_tma", 0), (b"splat_fused_max", 0), (b"splat_pf_rows", 8)):
+    for name, val in ((b"splat_tma", 0), (b"splat_fused_max", 0), (b"splat_pf_rows", 8), (b"splat_snake", 0)):
         old = lib.fldr_get_option(name)
         lib.fldr_set_option(name, val)
         assert lib.fldr_splat_fwd_workspace_bytes(3, 1, 3, 2304, 4096) == ws0

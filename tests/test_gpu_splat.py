@@ -375,3 +375,28 @@ def test_cfg5_training_shapes_vs_oracle(cuda_lib):
     yfo, gifo, _, _ = so.function_softsplat_grads(xf, ff, None, "softmax", gf_)
     assert_splat_close(yf, yfo, "cfg5 feature out")
     assert_splat_close(gif, gifo, "cfg5 feature grad_input")
+
+
+@pytest.mark.parametrize("N,C,H,W,metric", [(1, 3, 96, 200, True), (3, 3, 40, 136, True), (2, 8, 33, 128, False)])
+@pytest.mark.parametrize("regime", ["F1", "F2", "FB"])
+def test_pass_order_and_prefetch_options_agree(cuda_lib, tile_everywhere, N, C, H, W, metric, regime):
+    """The alternating row order of the three passes (splat_snake, default), the front-to-back order with cudaMemsetAsync and
+    the L2 prefetch of accumulator rows are scheduling choices: every combination must give the oracle's result (the image-splat
+    shape C = 3 + metric also exercises the cross / carry-to-E merges of the tile scatter under stretch, shear and border flows)."""
+    import fldr_vfi_b200.softSplat as S
+    x = (synth.image(N, C, H, W, seed=5) if C == 3 else synth.features(N, C, H, W, seed=5))
+    fl = synth.flow(N, H, W, regime, seed=6) * (6.0 if regime == "F1" else 1.0)
+    z = synth.metric(N, H, W, seed=7) if metric else None
+    ref = so.function_softsplat(x, fl, z, "softmax")
+    old = {k: cuda_lib.fldr_get_option(k) for k in (b"splat_snake", b"splat_pf_rows")}
+    try:
+        for snake in (1, 0):
+            for pf in (0, 3, -1):
+                cuda_lib.fldr_set_option(b"splat_snake", snake)
+                cuda_lib.fldr_set_option(b"splat_pf_rows", pf)
+                with torch.no_grad():
+                    y = S.FunctionSoftsplat(x.cuda(), fl.cuda(), None if z is None else z.cuda(), "softmax")
+                assert_splat_close(y, ref, f"snake={snake} pf={pf} {regime}")
+    finally:
+        for k, v in old.items():
+            cuda_lib.fldr_set_option(k, v)
