@@ -372,10 +372,10 @@ __global__ void __launch_bounds__(tile::TW, 6) splat_scatter_tile_kernel(const _
         // flow moved one cell to the left between the rows - or is flushed
         const bool vm = tT == prev_t;
         // (extra matches only for the image splat, QS == 1: its accumulator is DRAM-sized and the pass is bound by the number of
-        //  32-byte sectors its reductions touch - 16.2 M -> 14.3 M at 4K, 120 -> 113 us; the L2-resident feature splats are
+        //  32-byte sectors its reductions touch - 16.2 M -> 13.6 M at 4K, 120 -> 111 us; the L2-resident feature splats are
         //  latency-bound and only pay for the extra instructions)
         const bool vme = QS == 1 && prev_t == tT + 1;    // never true for kSent (tT + 1 stays far below any cell)
-        red4_at(rq, (vm || vme) ? kSent : prev_t, pw);
+        if (QS != 1) red4_at(rq, vm ? kSent : prev_t, pw);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             tW[j] = vm ? tW[j] + pw[j] : tW[j];
@@ -389,6 +389,17 @@ __global__ void __launch_bounds__(tile::TW, 6) splat_scatter_tile_kernel(const _
         for (int j = 0; j < 4; ++j) {
             rt4[j] = __shfl_sync(0xffffffffu, tE[j], src_lane);
             rb4[j] = __shfl_sync(0xffffffffu, bE[j], src_lane);
+        }
+        if (QS == 1) {
+            // a carried corner that found no partner in its own column often IS the cell of a corner just received (under vertical
+            // shear the left neighbour's top-E corner lands where this column's previous row put its bottom-W): join them, else flush
+            const bool vrT = !(vm || vme) && prev_t == rT, vrB = !(vm || vme) && prev_t == rB;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                rt4[j] = vrT ? rt4[j] + pw[j] : rt4[j];
+                rb4[j] = vrB ? rb4[j] + pw[j] : rb4[j];
+            }
+            red4_at(rq, (vm || vme || vrT || vrB) ? kSent : prev_t, pw);
         }
         // straight matches (same row) and cross matches (the flow's vertical shear moved the neighbour one row up or down: its top-E
         // corner is my bottom-W cell, or its bottom-E corner my top-W cell).  A received corner matches at most one of my two cells.
