@@ -445,10 +445,56 @@ __global__ void __launch_bounds__(256) splat_zero_kernel(float4* __restrict__ ac
 // PX float4 loads of the accumulator (+ PX of the quad holding the normaliser), 4 channel-plane stores of PX floats.
 //   softSplat.py:343-349: norm==0 -> 1, divide, (y - 0.5) * 2 (post-scale in every mode but RAW).
 // ------------------------------------------------------------------------------------------------
-template <int PX>
+template <int PX, bool DISCARD = false>
 __global__ void __launch_bounds__(128) splat_normalise_kernel(const float* __restrict__ acc, float* __restrict__ out,
                                                               float* __restrict__ norm_out, SplatGeom g, int Q) {
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
+    if (DISCARD) {
+        // The accumulator is dead once it has been read.  Whatever part of it is still dirty in L2 would be written back to DRAM
+        // for nothing: after every thread of the CTA has CONSUMED its loads (the barrier below), the 128-byte lines that lie
+        // entirely inside this CTA's cells are dropped from L2 without a write-back (discard.global.L2).  Single-plane frames only
+        // (Q == 1): nobody else reads these cells.
+        const int y = blockIdx.y, n = blockIdx.z;
+        const int P = g.W + 2;
+        const long long HW = (long long)g.H * g.W;
+        const float4* row = reinterpret_cast<const float4*>(acc) + ((long long)n * g.H + y) * P + 1;
+        float4 s4[PX];
+        float yv[4][PX], nrm[PX];
+        const bool live = x < g.W;
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < PX; ++k) s4[k] = __ldcs(row + x + k);
+            const int slot = g.C & 3;
+#pragma unroll
+            for (int k = 0; k < PX; ++k) {
+                nrm[k] = slot == 0 ? s4[k].x : slot == 1 ? s4[k].y : slot == 2 ? s4[k].z : s4[k].w;
+                const float d = norm_recip(nrm[k]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float sv = j == 0 ? s4[k].x : j == 1 ? s4[k].y : j == 2 ? s4[k].z : s4[k].w;
+                    yv[j][k] = post_scale(sv, d, false, true);
+                }
+            }
+        }
+        __syncthreads();                     // every load of the CTA has been consumed
+        {
+            const int c0 = blockIdx.x * blockDim.x * PX;                                   // first pixel of the CTA in this row
+            const int nc = min(g.W - c0, (int)blockDim.x * PX);
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(row + c0), a1 = a0 + (uintptr_t)nc * 16;
+            const uintptr_t l0 = (a0 + 127) & ~(uintptr_t)127;
+            const uintptr_t line = l0 + (uintptr_t)threadIdx.x * 128;
+            if (line + 128 <= a1) asm volatile("discard.global.L2 [%0], 128;" ::"l"(line) : "memory");
+        }
+        if (live) {
+            const long long pix = (long long)y * g.W + x;
+            if (norm_out) vstore<PX>(norm_out + (long long)n * HW + pix, nrm);
+            float* op = out + (long long)n * g.C * HW + pix;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < g.C) vstore<PX>(op + (long long)j * HW, yv[j]);
+        }
+        return;
+    }
     if (x >= g.W) return;       // PX > 1 only when W % PX == 0
     const int y = blockIdx.y;
     const int q = blockIdx.z % Q, n = blockIdx.z / Q;
@@ -890,7 +936,10 @@ static int launch_normalise(const FwdPlan& p, float* acc, float* out, float* nor
     const int N = g.N, Q = p.Q;
     const bool px4 = (g.W % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                      (!norm || (reinterpret_cast<uintptr_t>(norm) & 15) == 0);
-    if (px4) {
+    if (px4 && Q == 1 && g.CA > g.C && g.mode != FLDR_SPLAT_RAW && get_option(kOptSplatSnake) != 0) {
+        dim3 grid((unsigned)((g.W / 4 + 127) / 128), g.H, N);
+        splat_normalise_kernel<4, true><<<grid, 128, 0, s>>>(acc, out, norm, g, Q);
+    } else if (px4) {
         dim3 grid((unsigned)((g.W / 4 + 127) / 128), g.H, N * Q);
         splat_normalise_kernel<4><<<grid, 128, 0, s>>>(acc, out, norm, g, Q);
     } else {
