@@ -16,3 +16,5 @@ FLDR_B200_NO_EXT=1 timeout 300 python tools/overhead_probe.py > gpurun_out/r2_ho
 timeout 300 python tools/splat_probe.py > gpurun_out/r2_splat_probe.txt 2>&1
 timeout 300 python tools/bwd_probe.py > gpurun_out/r2_bwd_probe.txt 2>&1
 tail -c 300 gpurun_out/r2_bench_full.json; echo; cat gpurun_out/r2_train_probe.txt
+# the image splat's traffic as the running step sees it (the three passes hand accumulator lines to each other through L2: no cache flush between kernels)
+timeout 600 ncu --cache-control none --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"splat_zero|splat_scatter_tile|splat_normalise" -c 90 --csv --log-file gpurun_out/r2_traffic_warm.csv python bench.py --steps 1 --warmup 2 --no-cpu-baseline --no-ref-gpu --no-fldrnet > /dev/null 2>&1
