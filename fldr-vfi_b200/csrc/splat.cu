@@ -15,12 +15,12 @@
 //
 // Paths (fldr_splat_fwd picks; DESIGN.md section 4.1 has the measurements behind each choice)
 //   tiny frames    splat_fused_small_kernel: zero + scatter + normalise in one cooperative launch
-//   default        cudaMemsetAsync + splat_scatter_tile_kernel (inputs staged by TMA, lean merged-reduction body)
-//                  + splat_normalise_kernel
+//   default        splat_zero_kernel (front to back, L2 eviction hints) + splat_scatter_tile_kernel (back to front; inputs staged by
+//                  TMA, merged reductions) + splat_normalise_kernel (front to back; drops the dead accumulator lines from L2)
 //   odd views      the same three passes with splat_scatter_merged_kernel (plain loads): rows that are not 16-byte aligned,
 //                  non-unit pixel stride, metric together with >= 4 channels
-// (A single-launch streaming variant with an L2-resident ring accumulator was built and measured in round 2; it moved
-//  322 MB instead of 848 MB through DRAM but lost on time - profiles/r2_splat_streaming_negative_result.txt.)
+// (Single-launch variants that keep the accumulator in L2 - streaming ring, tile owner, cluster per sample - were built and
+//  measured in round 2 and lost on time: profiles/r2_splat_*_negative_result.txt.)
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>

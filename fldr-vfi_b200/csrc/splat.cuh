@@ -1,5 +1,4 @@
-// Declarations shared by the splat translation units (splat.cu: whole-frame and small-frame paths, backward;
-// splat_ring.cu: single-launch streaming path with the L2-resident ring accumulator).
+// Declarations shared by the splat kernels (splat.cu: whole-frame and small-frame paths, backward).
 #pragma once
 #include "common.cuh"
 
@@ -18,7 +17,7 @@ __host__ __device__ inline bool mode_has_norm(int mode) {
 }
 
 // softSplat.py:343-349 for one accumulated value: hole fix-up, divide, post-scale.  Every path (normalise pass, small-frame
-// kernel, ring kernel) goes through these two helpers, so a call gives the same bits apart from the summation order
+// kernel) goes through these two helpers, so a call gives the same bits apart from the summation order
 // whichever path serves it.  The divide is one reciprocal per pixel (rcp.approx.f32: 1 ulp, subnormals handled) and a
 // multiply per channel - within 2 ulp of the reference's S / norm, far inside the summation-order noise; an IEEE division
 // per channel made the normalise pass instruction-bound.
