@@ -230,10 +230,11 @@ __device__ __forceinline__ void scatter_rows(const View4& in, const View4& flow,
 
 template <int WKIND, bool PRE, int QS>
 __global__ void __launch_bounds__(128, FLDR_SCATTER_MIN_CTAS) splat_scatter_merged_kernel(View4 in, View4 flow, View4 metric,
-                                                                   float* __restrict__ acc, SplatGeom g, int Q, int pf_rows, int R) {
+                                                                   float* __restrict__ acc, SplatGeom g, int Q, int pf_rows, int R, int flip) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int yb = blockIdx.y * R;
-    const int q = blockIdx.z % Q, n = blockIdx.z / Q;
+    const int yb = (flip ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y) * R;          // back to front, like the tile kernel
+    const int bz = flip ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+    const int q = bz % Q, n = bz / Q;
     PlaneAcc pa;
     pa.P = g.W + 2;
     pa.base = reinterpret_cast<float4*>(acc) + (long long)(n * Q + q) * g.H * pa.P;
@@ -1054,7 +1055,7 @@ static int launch_forward(const FwdPlan& p, const View4& vin, const View4& vfl, 
         while (R > 4 && per_row_ctas * ((H + R - 1) / R) < two_waves) R >>= 1;
         dim3 grid((W + bx - 1) / bx, (H + R - 1) / R, N * Q);
 #define FLDR_LAUNCH_SCATTER2(WK_, PRE_, QS_) \
-    splat_scatter_merged_kernel<WK_, PRE_, QS_><<<grid, bx, 0, s>>>(vin, vfl, vme, acc, g, Q, pf, R)
+    splat_scatter_merged_kernel<WK_, PRE_, QS_><<<grid, bx, 0, s>>>(vin, vfl, vme, acc, g, Q, pf, R, snake)
 #define FLDR_LAUNCH_SCATTER(WK_, PRE_)                                       \
     do {                                                                     \
         if (qs == 1) FLDR_LAUNCH_SCATTER2(WK_, PRE_, 1);                     \
