@@ -296,13 +296,14 @@ __device__ __forceinline__ float exp_splat(float z) {
     return fmaf(p, e * 0.6931471805599453f, p);
 }
 
-template <int WKIND, bool PRE, int QS>
+template <int WKIND, bool PRE, int QS, int TR>
 __global__ void __launch_bounds__(tile::TW, 6) splat_scatter_tile_kernel(const __grid_constant__ CUtensorMap tm_in,
                                                                          const __grid_constant__ CUtensorMap tm_flow,
                                                                          const __grid_constant__ CUtensorMap tm_metric,
                                                                          float* __restrict__ acc, SplatGeom g, int Q, int nbox,
                                                                          int pf_rows, int flip) {
     using namespace tile;
+    constexpr int R = TR;                                // rows of a tile (shadows tile::R)
     __shared__ __align__(128) float st[PLANES * R * TW];
     __shared__ uint64_t bar;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -956,10 +957,10 @@ static bool view_tma_ok(const View4& v) {
     return v.sw == 1 && v.sh > 0 && v.sc > 0 && v.sn > 0 && (v.sh % 4) == 0 && (v.sc % 4) == 0 && (v.sn % 4) == 0 && aligned16(v.p);
 }
 // [N][C][H][W] view -> 4-D tensor map with an [nbox][8][128] box
-static bool encode_view(CUtensorMap* map, const View4& v, int N, int C, int H, int W, int nbox) {
+static bool encode_view(CUtensorMap* map, const View4& v, int N, int C, int H, int W, int nbox, int tile_rows) {
     const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)N};
     const uint64_t strides[3] = {(uint64_t)v.sh * 4, (uint64_t)v.sc * 4, (uint64_t)v.sn * 4};
-    const uint32_t box[4] = {(uint32_t)tile::TW, (uint32_t)tile::R, (uint32_t)nbox, 1u};
+    const uint32_t box[4] = {(uint32_t)tile::TW, (uint32_t)tile_rows, (uint32_t)nbox, 1u};
     return encode_tensor_map_4d(map, v.p, dims, strides, box);
 }
 
@@ -1024,20 +1025,24 @@ static int launch_forward(const FwdPlan& p, const View4& vin, const View4& vfl, 
     bool tiled = get_option(kOptSplatStream) != 0 && view_tma_ok(vin) && view_tma_ok(vfl) && (!g.has_metric || (view_tma_ok(vme) && g.C < 4));
     CUtensorMap tm_in, tm_fl, tm_me;
     const int nbox = (Q == 1) ? g.C : 4;               // channels per input box
+    // tile height: 8 source rows; 4 for a single DRAM-sized image plane (more, shorter CTAs: 163 -> 160 us on the 4K frame; batches
+    // and the L2-resident feature splats measured 2 - 4 % slower with 4 and keep 8)
+    const int tr = (qs == 1 && N * Q == 1 && (size_t)n4 * 16 > (48u << 20)) ? 4 : tile::R;
     if (tiled) {
-        tiled = encode_view(&tm_in, vin, N, g.C, H, W, nbox) && encode_view(&tm_fl, vfl, N, 2, H, W, 2);
-        if (tiled && g.has_metric) tiled = encode_view(&tm_me, vme, N, 1, H, W, 1);
+        tiled = encode_view(&tm_in, vin, N, g.C, H, W, nbox, tr) && encode_view(&tm_fl, vfl, N, 2, H, W, 2, tr);
+        if (tiled && g.has_metric) tiled = encode_view(&tm_me, vme, N, 1, H, W, 1, tr);
         if (tiled && !g.has_metric) tm_me = tm_fl;
     }
     if (tiled) {
-        dim3 grid((W + tile::TW - 1) / tile::TW, (H + tile::R - 1) / tile::R, N * Q);
-#define FLDR_LAUNCH_TILE2(WK_, PRE_, QS_) \
-    splat_scatter_tile_kernel<WK_, PRE_, QS_><<<grid, tile::TW, 0, s>>>(tm_in, tm_fl, tm_me, acc, g, Q, nbox, pf, snake)
+        dim3 grid((W + tile::TW - 1) / tile::TW, (H + tr - 1) / tr, N * Q);
+#define FLDR_LAUNCH_TILE2(WK_, PRE_, QS_, TR_) \
+    splat_scatter_tile_kernel<WK_, PRE_, QS_, TR_><<<grid, tile::TW, 0, s>>>(tm_in, tm_fl, tm_me, acc, g, Q, nbox, pf, snake)
 #define FLDR_LAUNCH_TILE(WK_, PRE_)                                       \
     do {                                                                  \
-        if (qs == 1) FLDR_LAUNCH_TILE2(WK_, PRE_, 1);                     \
-        else if (qs == 2) FLDR_LAUNCH_TILE2(WK_, PRE_, 2);                \
-        else FLDR_LAUNCH_TILE2(WK_, PRE_, 0);                             \
+        if (qs == 1 && tr == 4) FLDR_LAUNCH_TILE2(WK_, PRE_, 1, 4);       \
+        else if (qs == 1) FLDR_LAUNCH_TILE2(WK_, PRE_, 1, tile::R);       \
+        else if (qs == 2) FLDR_LAUNCH_TILE2(WK_, PRE_, 2, tile::R);       \
+        else FLDR_LAUNCH_TILE2(WK_, PRE_, 0, tile::R);                    \
     } while (0)
         if (wkind == 1) FLDR_LAUNCH_TILE(1, true);
         else if (wkind == 2) FLDR_LAUNCH_TILE(2, false);
